@@ -1,0 +1,35 @@
+"""GPU scratch check of the tcgen05 path: self-tests, then bf16 forward vs oracle."""
+import ctypes as C, json, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from adafortitran_b200 import _capi
+from oracle import aft_oracle as O
+from tests import util
+
+def selftests():
+    torch.cuda.init(); torch.zeros(1, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for which in (0, 1, 2):
+        err = C.c_double(-1)
+        rc = _capi.lib().aft_selftest(which, C.byref(err), C.c_void_p(st))
+        print(json.dumps({"selftest": which, "rc": rc, "max_err": err.value, "msg": _capi.lib().aft_last_error().decode()}), flush=True)
+
+def forward_check(kind="ada", B=8):
+    sd = util.ada_weights()
+    if kind != "ada": sd = util.forti_weights(sd)
+    p, snr, ds, dop = O.synthetic_batch(B, seed=3)
+    ref = O.forward(util.oracle_cfg(kind), sd, p, snr, ds, dop)
+    m = util.make_model(kind, weights=sd, precision="bf16")
+    md = util.meta(snr, ds, dop) if kind == "ada" else None
+    with torch.no_grad():
+        y = m(torch.from_numpy(p), md)
+    torch.cuda.synchronize()
+    y = y.cpu().numpy()
+    print(json.dumps({"bf16_forward": kind, "B": B, "normwise": O.normwise_err(y, ref), "rel_db": O.rel_err_db(y, ref),
+                      "finite": bool(np.isfinite(y.view(np.float32)).all())}), flush=True)
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "self"): selftests()
+    if what in ("all", "fwd"):
+        forward_check("forti", 2); forward_check("forti", 160); forward_check("ada", 8)

@@ -65,6 +65,8 @@ EXPORTS = {
                                    C.c_int64, C.c_int]),
     "aft_error_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "aft_launch_count": (C.c_int64, []),
+    "aft_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "aft_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "aft_selftest": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_void_p]),
 }
 

@@ -97,6 +97,11 @@ struct AftHandle {
   HeadPack head{};
   std::vector<LayerPackF32> layers;
   TcWeights tc{};               // bf16 operand images (tc_encoder.cuh)
+  // stage profile (aft_profile_enable / aft_profile_read)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // groups of 4: start, after frontend, after encoder, after head
+  size_t prof_used = 0;
+  int64_t prof_launches[3] = {0, 0, 0};
   // aft_forward_host resources (lazy)
   struct HostLane {
     cudaStream_t stream = nullptr;
@@ -220,6 +225,19 @@ bool copy_to(const float* src, const float* dst, int n, cudaStream_t st, const c
   return check_launch(name);
 }
 
+// records the next profile event on `st` (no-op unless profiling is enabled)
+void prof_mark(AftHandle* h, cudaStream_t st) {
+  if (!h->profile) return;
+  if (h->prof_used == h->prof_events.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    h->prof_events.push_back(e);
+  }
+  cudaEventRecord(h->prof_events[h->prof_used++], st);
+}
+
+void prof_mark_cb(void* ctx, cudaStream_t st) { prof_mark(static_cast<AftHandle*>(ctx), st); }
+
 int forward_chunk_f32(AftHandle* h, const float2* pilots, const float* snr, const float* ds, const float* dop,
                       float2* out, int64_t bc, float* ws, cudaStream_t st) {
   const int64_t nseq = 2 * bc, M = nseq * kS;
@@ -228,7 +246,9 @@ int forward_chunk_f32(AftHandle* h, const float2* pilots, const float* snr, cons
   float* qkv = hbuf + align_up((size_t)nseq * kS * kD, 64);
   float* att = qkv + align_up((size_t)nseq * kS * 3 * kD, 64);
   float* ffn = qkv;
+  prof_mark(h, st);
   if (!launch_frontend(h->front, pilots, snr, ds, dop, enh, hbuf, nullptr, bc, st)) return AFT_ERR_CUDA;
+  prof_mark(h, st);
   for (const LayerPackF32& L : h->layers) {
     if (!launch_gemm_f32(kEpiBias, hbuf, L.in_w, L.in_b, qkv, M, 3 * kD, kD, 0, nullptr, nullptr, nullptr, st)) return AFT_ERR_CUDA;
     if (!launch_attn_f32(qkv, att, nseq, st)) return AFT_ERR_CUDA;
@@ -236,7 +256,10 @@ int forward_chunk_f32(AftHandle* h, const float2* pilots, const float* snr, cons
     if (!launch_gemm_f32(kEpiBiasAct, hbuf, L.l1_w, L.l1_b, ffn, M, kFF, kD, h->cfg.activation, nullptr, nullptr, nullptr, st)) return AFT_ERR_CUDA;
     if (!launch_gemm_f32(kEpiBiasResLn, ffn, L.l2_w, L.l2_b, hbuf, M, kD, kFF, 0, hbuf, L.n2_w, L.n2_b, st)) return AFT_ERR_CUDA;
   }
+  prof_mark(h, st);
   if (!launch_head(h->head, hbuf, enh, out, bc, st)) return AFT_ERR_CUDA;
+  prof_mark(h, st);
+  if (h->profile) { h->prof_launches[0] += 1; h->prof_launches[1] += 5 * (int64_t)h->layers.size(); h->prof_launches[2] += 1; }
   return AFT_OK;
 }
 
@@ -299,6 +322,7 @@ void aft_destroy(AftHandle* h) {
     if (ln.ws) cudaFree(ln.ws);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   tc_weights_free(h->tc);
   if (h->arena) cudaFree(h->arena);
   delete h;
@@ -405,8 +429,10 @@ int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float*
     if (precision == AFT_FP32) {
       rc = forward_chunk_f32(h, pin + c0 * kPilots, s0, s1, s2, pout + c0 * kPix, bc, static_cast<float*>(workspace), st);
     } else {
+      TcProfileHook hook{h->profile ? &prof_mark_cb : nullptr, h};
       rc = tc_forward_chunk(h->tc, h->front, h->head, h->cfg.activation, h->sm_count, pin + c0 * kPilots, s0, s1, s2,
-                            pout + c0 * kPix, bc, workspace, st) ? AFT_OK : AFT_ERR_CUDA;
+                            pout + c0 * kPix, bc, workspace, st, hook) ? AFT_OK : AFT_ERR_CUDA;
+      if (h->profile) { h->prof_launches[0] += 1; h->prof_launches[1] += 1; h->prof_launches[2] += 1; }
     }
     if (rc != AFT_OK) return rc;
   }
@@ -477,6 +503,30 @@ int aft_error_sums(const void* est, const void* truth, int64_t count, double* su
   if (count == 0) return AFT_OK;
   return launch_error_sums(static_cast<const float2*>(est), static_cast<const float2*>(truth), count, sums,
                            static_cast<cudaStream_t>(stream)) ? AFT_OK : AFT_ERR_CUDA;
+}
+
+int aft_profile_enable(AftHandle* h, int enable) {
+  if (!h) { set_error("aft_profile_enable: NULL handle"); return AFT_ERR_INVALID; }
+  h->profile = enable != 0;
+  h->prof_used = 0;
+  h->prof_launches[0] = h->prof_launches[1] = h->prof_launches[2] = 0;
+  return AFT_OK;
+}
+
+int aft_profile_read(AftHandle* h, double* ms, int64_t* launches) {
+  if (!h || !ms || !launches) { set_error("aft_profile_read: NULL argument"); return AFT_ERR_INVALID; }
+  ms[0] = ms[1] = ms[2] = 0.0;
+  for (size_t i = 0; i + 3 < h->prof_used; i += 4) {
+    AFT_CUDA(cudaEventSynchronize(h->prof_events[i + 3]));
+    for (int s = 0; s < 3; ++s) {
+      float t = 0.f;
+      AFT_CUDA(cudaEventElapsedTime(&t, h->prof_events[i + s], h->prof_events[i + s + 1]));
+      ms[s] += t;
+    }
+  }
+  for (int s = 0; s < 3; ++s) { launches[s] = h->prof_launches[s]; h->prof_launches[s] = 0; }
+  h->prof_used = 0;
+  return AFT_OK;
 }
 
 int aft_selftest(int which, double* max_err, void* stream) {

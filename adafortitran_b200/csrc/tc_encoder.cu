@@ -6,10 +6,17 @@
 // Per sequence the only HBM traffic is the 72 KB input image and the 140 KB fp32 result; weights (256 KB bf16
 // per layer) are streamed from L2 by 1-D bulk copies (cp.async.bulk) into a small ring.
 //
-//   warp 0      : producer  -- bulk copies (sequence image, weight slices), mbarrier expect_tx
-//   warp 1      : MMA issuer -- one thread issues every tcgen05.mma; owns the TMEM allocation
-//   warps 2..9  : compute    -- TMEM -> registers epilogues: bias, softmax, 1/l, residual + LayerNorm, GELU;
-//                               write the next operand image (bf16) to shared memory / P to TMEM
+//   warpgroup 0 : warp 0 = producer (bulk copies + expect_tx), warp 1 = MMA issuer (one thread issues every
+//                 tcgen05.mma, owns the TMEM allocation); warps 2,3 idle.  Registers shrunk with setmaxnreg.
+//   warpgroups 1,2 : 8 compute warps -- TMEM -> registers epilogues (bias, softmax, 1/l, residual + LayerNorm,
+//                 GELU), writing the next operand image (bf16) to shared memory / P to TMEM.  Registers grown
+//                 to 224 so a thread can hold a 144-wide score row or a 128-wide LayerNorm row.
+//
+// The MMA issuer and the compute warps each run a static program; they meet only through mbarriers
+// (tcgen05.commit -> "done" barriers; one arrive per compute warp -> "ready/free" barriers), so tensor-core work
+// for the next tile is in flight while the epilogue of the current one runs:  S(t+1) is issued as soon as S(t) is
+// in registers, P.V(t) runs under the exponentials of tile t+1, QKV(g+1) queues behind P.V of head g, FFN1 tiles
+// and FFN2 partial products are double buffered.
 //
 // All GEMMs use M = 128 row tiles (3 per sequence; the rows past 280 of the third tile read whatever follows in
 // shared memory -- rows of A are independent, the corresponding accumulator lanes are never read).
@@ -21,10 +28,11 @@
 //                           | out_proj / FFN weight ring: 3 slots x 16384
 //   W    [ 202752, 227328)  in_proj slice of one head: rows q_g | k_g | v_g (96 x K=128)
 //   MISC [ 227328, 230400)  mbarriers, TMEM base, softmax max / sum exchange
-// Tensor memory map (columns): S [0,288)  P [288,432) (bf16 pairs)  O_acc [432,464);
+// Tensor memory map (columns): S [0,288)  P [288,432) (bf16 pairs)  O_acc x2 [432,464) [464,496);
 //   QKV accumulators alias S; out_proj / FFN2 accumulators [0,384); FFN1 accumulators [384,448) [448,512).
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "tc_encoder.cuh"
@@ -37,7 +45,9 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 384;      // 3 warpgroups: [producer, MMA, idle, idle] + 2 x 4 compute warps
+constexpr int kRegsCtrl = 56;        // setmaxnreg budget of warpgroup 0
+constexpr int kRegsCompute = 224;    // setmaxnreg budget of the compute warpgroups  (128*56 + 256*224 = 64512 <= 65536)
 constexpr int kTcMaxLayers = 8;
 constexpr int kVecPerLayer = 1408;   // b_in 384 | b_out 128 | b_l1 256 | b_l2 128 | n1_w n1_b n2_w n2_b 4x128
 constexpr int kVecBOut = 384, kVecBL1 = 512, kVecBL2 = 768, kVecN1W = 896, kVecN1B = 1024, kVecN2W = 1152, kVecN2B = 1280;
@@ -50,13 +60,35 @@ constexpr uint32_t kWInSlice = 24576;           // 2 chunks x 96 rows x 128 B
 constexpr uint32_t kMiscBytes = 3072;
 constexpr uint32_t kTcSmemBytes = OFF_MISC + kMiscBytes + 1024;   // + alignment slack
 
-// MISC offsets
-constexpr uint32_t MB_MMA_DONE = 0, MB_OPS_READY = 8, MB_X_FULL = 16, MB_X_FREE = 24, MB_ATTN_DONE = 32;
-constexpr uint32_t MB_W_FULL = 40;    // 4 barriers: [0] = in_proj slot, [1..3] = ring slots
-constexpr uint32_t MB_W_EMPTY = 72;   // 4 barriers
-constexpr uint32_t MISC_TMEM_PTR = 128;
-constexpr uint32_t MISC_XMAX = 256;   // [2][128] f32
-constexpr uint32_t MISC_XSUM = 1280;  // [2][128] f32
+// mbarriers (byte offsets inside MISC).  Protocol rule: a waiter tests phase parity, so no barrier may complete two
+// phases ahead of its waiter; every barrier below is lag <= 1 by construction (per-buffer barriers where the consumer
+// waits lazily: O accumulators, FFN1 accumulators, hidden buffers).  "commit" barriers have count 1 (tcgen05.commit or expect_tx),
+// "warp" barriers have count 8 (lane 0 of every compute warp arrives).
+enum : uint32_t {
+  MB_X_FULL = 0,       // commit: sequence image landed
+  MB_X_FREE = 8,       // warp  : last LayerNorm of the sequence done, X may be replaced
+  MB_ATTN_DONE = 16,   // commit: last P.V of the layer done -> Q/K/V images dead, ring may overwrite them
+  MB_W_FULL = 24,      // 4 x commit: [0] in_proj slot, [1..3] ring slots
+  MB_W_EMPTY = 56,     // 4 x commit
+  MB_QKV_DONE = 88,    // commit: QKV accumulators of head g complete
+  MB_QKV_READY = 96,   // warp  : Q/K/V images of head g written (and the accumulators read out)
+  MB_S_DONE = 104,     // commit: score tile complete
+  MB_S_LOADED = 112,   // warp  : score tile is in registers, S columns free
+  MB_P_READY = 120,    // warp  : P tile written to TMEM
+  MB_PV_DONE = 128,    // commit: P.V complete (P columns free, O accumulator valid)
+  MB_O_FREE = 136,     // 2 x warp : O accumulator buffer b read out, O image columns written
+  MB_OUT_DONE = 152,   // commit: out_proj accumulators complete
+  MB_X1_READY = 160,   // warp  : LayerNorm1 written to X
+  MB_F1_DONE = 168,    // 2 x commit: FFN1 accumulator buffer b complete
+  MB_F1_FREE = 184,    // 2 x warp  : FFN1 accumulator buffer b read out
+  MB_HID_READY = 200,  // warp  : hidden chunk image complete (all three row tiles)
+  MB_F2_DONE = 208,    // 2 x commit: FFN2 partial product over hidden buffer b complete (buffer free / final result)
+  MB_X2_READY = 224,   // warp  : LayerNorm2 written to X
+  MB_COUNT_BYTES = 232,
+};
+constexpr uint32_t MISC_TMEM_PTR = 256;
+constexpr uint32_t MISC_XMAX = 512;   // [2][128] f32
+constexpr uint32_t MISC_XSUM = 1536;  // [2][128] f32
 
 constexpr uint32_t TM_S = 0, TM_P = 288, TM_O = 432, TM_QKV = 0, TM_OUT = 0, TM_F1 = 384;
 
@@ -66,12 +98,31 @@ constexpr uint32_t kIdescPV = make_idesc_bf16(128, 32, false, true);     // B = 
 constexpr uint32_t kIdescN128 = make_idesc_bf16(128, 128, false, false);
 constexpr uint32_t kIdescN64 = make_idesc_bf16(128, 64, false, false);
 
-__constant__ float c_vec[kTcMaxLayers * kVecPerLayer];
+__constant__ __align__(16) float c_vec[kTcMaxLayers * kVecPerLayer];
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GELU(x) = x Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the bf16 rounding of the
+// result): Phi(-|x|) = 0.5 poly(t) exp(-x^2/2), t = 1/(1 + p|x|/sqrt2);  gelu = max(x,0) - |x| Phi(-|x|).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(ax, 0.3275911f * 0.70710678f, 1.0f));
+  const float e = ex2(x * x * (-0.5f * 1.4426950409f));
+  float p = 0.5f * 1.061405429f;
+  p = fmaf(p, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float y = p * t * e;
+  return fmaf(-ax, y, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
   lo = __uint_as_float(w << 16);
@@ -93,11 +144,27 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
+// 16-byte load from the constant bank that the compiler may not hoist (keeps the epilogues' live ranges short)
+__device__ __forceinline__ float4 ldc_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.const.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(__cvta_generic_to_constant(p)));
+  return v;
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// one arrival per compute warp: every lane has fenced its own TMEM / shared-memory accesses before calling
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
 
 // =============================================================================================
 // MMA issue helpers (called by the single issuing thread).  `sb` = 1024-aligned shared base address.
 // =============================================================================================
-// D[tile] (N cols at d_col) = A(image with 128-B rows, `a_rows` rows per K-chunk)[tile rows] . B(image, b_rows per chunk)^T
+// D (N cols at d_col) (+)= A(image with 128-B rows)[128 rows at a_base] . B(image at b_base)^T ; K = 16 * ksteps
 __device__ __forceinline__ void issue_gemm_sw128(uint32_t tmem, uint32_t d_col, uint32_t a_base, uint32_t a_chunk_bytes,
                                                  uint32_t b_base, uint32_t b_chunk_bytes, int ksteps, uint32_t idesc,
                                                  bool accumulate_first) {
@@ -117,166 +184,185 @@ __device__ __forceinline__ void issue_scores(uint32_t tmem, uint32_t sb, int t) 
     for (int ks = 0; ks < 2; ++ks)
       mma_ss(tmem + TM_S + nh * 144, desc_k_sw64(q + ks * 32), desc_k_sw64(k + nh * 144 * 64 + ks * 32), kIdescS, ks > 0);
 }
-// O_acc = P (TMEM, bf16 pairs) . V_g   (K = 288 keys = 18 steps, N = 32)
-__device__ __forceinline__ void issue_pv(uint32_t tmem, uint32_t sb) {
+// O_acc[buf] = P (TMEM, bf16 pairs) . V_g   (K = 288 keys = 18 steps, N = 32)
+__device__ __forceinline__ void issue_pv(uint32_t tmem, uint32_t sb, int obuf) {
   const uint32_t v = sb + OFF_QKV + 2 * kQkvPart;
 #pragma unroll 1
-  for (int ks = 0; ks < 18; ++ks) mma_ts(tmem + TM_O, tmem + TM_P + ks * 8, desc_mn_sw64(v + ks * 1024), kIdescPV, ks > 0);
+  for (int ks = 0; ks < 18; ++ks)
+    mma_ts(tmem + TM_O + obuf * 32, tmem + TM_P + ks * 8, desc_mn_sw64(v + ks * 1024), kIdescPV, ks > 0);
 }
 
 // =============================================================================================
-// compute-warp epilogues.  q = warp % 4 (TMEM lane quadrant), half = warpgroup (0: warps 2-5, 1: warps 6-9)
+// compute-warp epilogues.  q = warp % 4 (TMEM lane quadrant), half = compute warpgroup (0 or 1)
 // =============================================================================================
-// QKV accumulators of (head g, row tile t) -> + bias -> bf16 -> Q_g / K_g / V_g images (SWIZZLE_64B rows of 64 B)
-__device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, int l, int g, int t, int q, int lane) {
+// QKV accumulators of (head g, row tile t) -> + bias -> bf16 -> Q_g / K_g / V_g images (SWIZZLE_64B rows of 64 B).
+// The 96 accumulator columns [q_g | k_g | v_g] are split between the two compute warpgroups: 3 x 16 columns each.
+__device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, int l, int g, int t, int q, int half, int lane) {
   const int r = t * 128 + q * 32 + lane;
-  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + t * 96;
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + t * 96 + half * 48;
+  const int sw = (r >> 1) & 3;
 #pragma unroll
-  for (int part = 0; part < 3; ++part) {
-    uint32_t a[16], b[16];
-    tmem_ld16(taddr + part * 32, a);
-    tmem_ld16(taddr + part * 32 + 16, b);
+  for (int i = 0; i < 3; ++i) {
+    const int col = half * 48 + i * 16;        // column inside [q | k | v], a multiple of 16
+    const int part = col >> 5, c0 = col & 31;  // which matrix, first column inside its 32
+    uint32_t a[16];
+    tmem_ld16(taddr + i * 16, a);
     tmem_wait_ld();
-    const float* bias = c_vec + l * kVecPerLayer + part * 128 + g * 32;
-    uint32_t pk[16];
+    const float* bias = c_vec + l * kVecPerLayer + part * 128 + g * 32 + c0;
+    uint32_t pk[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      pk[j] = pack_bf16x2(__uint_as_float(a[2 * j]) + bias[2 * j], __uint_as_float(a[2 * j + 1]) + bias[2 * j + 1]);
-      pk[8 + j] = pack_bf16x2(__uint_as_float(b[2 * j]) + bias[16 + 2 * j], __uint_as_float(b[2 * j + 1]) + bias[16 + 2 * j + 1]);
-    }
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(a[2 * j]) + bias[2 * j], __uint_as_float(a[2 * j + 1]) + bias[2 * j + 1]);
     const uint32_t row = sb + OFF_QKV + part * kQkvPart + r * 64;
-    const int sw = (r >> 1) & 3;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) st_shared_v4(row + ((u ^ sw) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    const int u0 = c0 >> 3;
+    st_shared_v4(row + (((u0) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(row + (((u0 + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
   }
 }
 
-// softmax over the 280 keys of one query row; this thread covers 144 score columns (half 1: 136 valid).
-// Scores are already in log2 units (q rows of in_proj pre-scaled by log2(e)/sqrt(dh)).
-__device__ __forceinline__ void epi_softmax(uint32_t tmem, uint32_t sb, bool active, int q, int half, int lane) {
-  const int rt = q * 32 + lane;
+// Softmax of one score tile, split in the two halves the barrier protocol needs.
+// (1) load this thread's 144 score columns (half 1: 136 valid) and the half-row maximum
+__device__ __forceinline__ float softmax_load(uint32_t tmem, int q, int half, float (&v)[144]) {
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-  float v[144];
-  float m = -INFINITY;
-  if (active) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      uint32_t x[16];
-      tmem_ld16(lane_addr + TM_S + half * 144 + i * 16, x);
-      tmem_wait_ld();
+  for (int i = 0; i < 9; ++i) {
+    uint32_t x[16];
+    tmem_ld16(lane_addr + TM_S + half * 144 + i * 16, x);
+    tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[i * 16 + j] = __uint_as_float(x[j]);
-    }
-    if (half == 1) {
-#pragma unroll
-      for (int j = kS - 144; j < 144; ++j) v[j] = -INFINITY;   // keys 280..287 are padding
-    }
-#pragma unroll
-    for (int j = 0; j < 144; ++j) m = fmaxf(m, v[j]);
-    st_shared_f32(sb + OFF_MISC + MISC_XMAX + (half * 128 + rt) * 4, m);
+    for (int j = 0; j < 16; ++j) v[i * 16 + j] = __uint_as_float(x[j]);
   }
-  named_bar_sync(1 + q, 64);
-  if (active) {
-    m = fmaxf(m, ld_shared_f32(sb + OFF_MISC + MISC_XMAX + ((half ^ 1) * 128 + rt) * 4));
-    float sum = 0.f;
+  if (half == 1) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float p0 = ex2(v[i * 16 + 2 * j] - m), p1 = ex2(v[i * 16 + 2 * j + 1] - m);
-        sum += p0 + p1;
-        pk[j] = pack_bf16x2(p0, p1);
-      }
-      tmem_st8(lane_addr + TM_P + half * 72 + i * 8, pk);
-    }
-    tmem_wait_st();
-    st_shared_f32(sb + OFF_MISC + MISC_XSUM + (half * 128 + rt) * 4, sum);
+    for (int j = kS - 144; j < 144; ++j) v[j] = -INFINITY;   // keys 280..287 are padding
   }
+  float m = v[0];
+#pragma unroll
+  for (int j = 1; j < 144; ++j) m = fmaxf(m, v[j]);
+  return m;
+}
+// (2) exponentials in place (scores are in log2 units: q rows of in_proj pre-scaled by log2(e)/sqrt(dh)); returns the sum
+__device__ __forceinline__ float softmax_exp(float (&v)[144], float m) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 144; j += 2) {
+    v[j] = ex2(v[j] - m);
+    v[j + 1] = ex2(v[j + 1] - m);
+    s0 += v[j];
+    s1 += v[j + 1];
+  }
+  return s0 + s1;
+}
+// (3) P tile -> TMEM as bf16 pairs (A operand of P.V)
+__device__ __forceinline__ void softmax_store(uint32_t tmem, int q, int half, const float (&v)[144]) {
+  const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[i * 16 + 2 * j], v[i * 16 + 2 * j + 1]);
+    tmem_st8(lane_addr + TM_P + half * 72 + i * 8, pk);
+  }
+  tmem_wait_st();
 }
 
-// O_acc (128 x 32) of (head g, tile t) -> / l -> bf16 -> O image columns g*32 .. g*32+31 (this thread: 16 of them)
-__device__ __forceinline__ void epi_o(uint32_t tmem, uint32_t sb, int g, int t, int q, int half, int lane) {
-  const int rt = q * 32 + lane, r = t * 128 + rt;
-  const float l = ld_shared_f32(sb + OFF_MISC + MISC_XSUM + rt * 4) + ld_shared_f32(sb + OFF_MISC + MISC_XSUM + (128 + rt) * 4);
-  const float inv = 1.0f / l;
+// O accumulator (128 x 32) of (head g, tile t) -> / l -> bf16 -> O image columns g*32 .. g*32+31 (this thread: 16 of them)
+__device__ __forceinline__ void epi_o(uint32_t tmem, uint32_t sb, int g, int t, int obuf, float inv_l, int q, int half, int lane) {
+  const int r = t * 128 + q * 32 + lane;
   uint32_t a[16];
-  tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_O + half * 16, a);
+  tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_O + obuf * 32 + half * 16, a);
   tmem_wait_ld();
   uint32_t pk[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(a[2 * j]) * inv, __uint_as_float(a[2 * j + 1]) * inv);
+  for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(a[2 * j]) * inv_l, __uint_as_float(a[2 * j + 1]) * inv_l);
   const uint32_t row = sb + OFF_O + (g >> 1) * kXChunkBytes + r * 128;
   const int u0 = (g & 1) * 4 + half * 2;
   st_shared_v4(row + (((u0) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
   st_shared_v4(row + (((u0 + 1) ^ (r & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
 }
 
-// out_proj / linear2 accumulators (tile t, 128 columns) + bias + residual (X image) -> LayerNorm -> X image in place
-// (+ fp32 rows to h_out after the last layer).  One thread owns one full row: statistics need no exchange.
-__device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, int l, int which, int t, int q, int lane, float* h_out_seq) {
+// out_proj / linear2 accumulators (tile t) + bias + residual (X image) -> LayerNorm -> X image in place (+ fp32 rows to
+// h_out after the last layer).  A row is shared by the two threads (one per compute warpgroup) that own TMEM lane
+// `rt`: each handles 64 columns = one K-chunk of the image; mean and variance are combined through shared memory.
+__device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, int l, int which, int t, int q, int half, int lane,
+                                       uint32_t xchg_mine, uint32_t xchg_other, float* h_out_seq) {
   const int r = t * 128 + q * 32 + lane;
   const float* vec = c_vec + l * kVecPerLayer;
-  const float* bias = vec + (which == 1 ? kVecBOut : kVecBL2);
-  const float* gam = vec + (which == 1 ? kVecN1W : kVecN2W);
-  const float* bet = vec + (which == 1 ? kVecN1B : kVecN2B);
-  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_OUT + t * 128;
-  const uint32_t xrow = sb + OFF_X + r * 128;
-  float v[128];
+  const float* bias = vec + (which == 1 ? kVecBOut : kVecBL2) + half * 64;
+  const float* gam = vec + (which == 1 ? kVecN1W : kVecN2W) + half * 64;
+  const float* bet = vec + (which == 1 ? kVecN1B : kVecN2B) + half * 64;
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_OUT + t * 128 + half * 64;
+  const uint32_t xrow = sb + OFF_X + half * kXChunkBytes + r * 128;
+  float v[64];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     uint32_t a[16];
     tmem_ld16(taddr + i * 16, a);
     tmem_wait_ld();
 #pragma unroll
     for (int hu = 0; hu < 2; ++hu) {
       const int u = i * 2 + hu;   // 16-byte unit = 8 columns
-      const uint4 xr = ld_shared_v4(xrow + (u >> 3) * kXChunkBytes + (((u & 7) ^ (r & 7)) << 4));
+      const uint4 xr = ld_shared_v4(xrow + ((u ^ (r & 7)) << 4));
       float x[8];
       unpack_bf16x2(xr.x, x[0], x[1]); unpack_bf16x2(xr.y, x[2], x[3]);
       unpack_bf16x2(xr.z, x[4], x[5]); unpack_bf16x2(xr.w, x[6], x[7]);
+      const float4 b0 = ldc_v4(bias + u * 8), b1 = ldc_v4(bias + u * 8 + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[u * 8 + j] = __uint_as_float(a[hu * 8 + j]) + bias[u * 8 + j] + x[j];
+      for (int j = 0; j < 8; ++j) v[u * 8 + j] = __uint_as_float(a[hu * 8 + j]) + bb[j] + x[j];
     }
   }
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 128; ++j) s += v[j];
-  const float mean = s * (1.0f / 128.0f);
-  float qv = 0.f;
+  for (int j = 0; j < 64; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
+  const float psum = (s0 + s1) + (s2 + s3);
+  st_shared_f32(xchg_mine, psum);
+  named_bar_sync(1 + q, 64);
+  const float mean = (psum + ld_shared_f32(xchg_other)) * (1.0f / 128.0f);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 128; ++j) { const float d = v[j] - mean; qv = fmaf(d, d, qv); }
-  const float rstd = rsqrtf(qv * (1.0f / 128.0f) + 1e-5f);
+  for (int j = 0; j < 64; j += 4) {
+    const float d0 = v[j] - mean, d1 = v[j + 1] - mean, d2 = v[j + 2] - mean, d3 = v[j + 3] - mean;
+    q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+  }
+  const float pvar = (q0 + q1) + (q2 + q3);
+  st_shared_f32(xchg_mine + 1024, pvar);     // second exchange array (MISC_XSUM = MISC_XMAX + 1024)
+  named_bar_sync(1 + q, 64);
+  const float rstd = rsqrtf((pvar + ld_shared_f32(xchg_other + 1024)) * (1.0f / 128.0f) + 1e-5f);
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
+  for (int u = 0; u < 8; ++u) {
     float o[8];
+    const float4 g0 = ldc_v4(gam + u * 8), g1 = ldc_v4(gam + u * 8 + 4), e0 = ldc_v4(bet + u * 8), e1 = ldc_v4(bet + u * 8 + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (v[u * 8 + j] - mean) * rstd * gam[u * 8 + j] + bet[u * 8 + j];
-    st_shared_v4(xrow + (u >> 3) * kXChunkBytes + (((u & 7) ^ (r & 7)) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    for (int j = 0; j < 8; ++j) o[j] = fmaf((v[u * 8 + j] - mean) * rstd, gg[j], ee[j]);
+    st_shared_v4(xrow + ((u ^ (r & 7)) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                 pack_bf16x2(o[6], o[7]));
     if (h_out_seq != nullptr && r < kS) {
-      float4* dst = reinterpret_cast<float4*>(h_out_seq + r * kD + u * 8);
+      float4* dst = reinterpret_cast<float4*>(h_out_seq + r * kD + half * 64 + u * 8);
       dst[0] = make_float4(o[0], o[1], o[2], o[3]);
       dst[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
   }
 }
 
-// FFN1 accumulators (chunk c = 64 hidden units, tile t; this thread: 32 of them) + bias -> GELU / ReLU -> hidden image
-__device__ __forceinline__ void epi_act(uint32_t tmem, uint32_t sb, int l, int c, int t, int buf, int act, int q, int half, int lane) {
-  const int r = t * 128 + q * 32 + lane;
+// FFN1 accumulators (chunk c = 64 hidden units, tile t; this thread: 32 of them): load + bias
+__device__ __forceinline__ void act_load(uint32_t tmem, int l, int c, int buf, int q, int half, float (&f)[32]) {
   const float* bias = c_vec + l * kVecPerLayer + kVecBL1 + c * 64 + half * 32;
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_F1 + buf * 64 + half * 32;
   uint32_t a[16], b[16];
   tmem_ld16(taddr, a);
   tmem_ld16(taddr + 16, b);
   tmem_wait_ld();
-  float f[32];
 #pragma unroll
   for (int j = 0; j < 16; ++j) { f[j] = __uint_as_float(a[j]) + bias[j]; f[16 + j] = __uint_as_float(b[j]) + bias[16 + j]; }
+}
+// GELU / ReLU -> bf16 -> hidden chunk image (K-chunk c of FFN2's A operand)
+__device__ __forceinline__ void act_store(uint32_t sb, int c, int t, int act, int q, int half, int lane, float (&f)[32]) {
+  const int r = t * 128 + q * 32 + lane;
   if (act == AFT_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -300,6 +386,12 @@ struct EncParams {
   int64_t nseq;
 };
 
+// use counter of an mbarrier on one side of the protocol: wait()/done() walk the phases in order
+struct Phase {
+  uint32_t n = 0;
+  __device__ __forceinline__ void wait(uint32_t bar) { mbar_wait(bar, n & 1); ++n; }
+};
+
 __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -307,12 +399,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
   const uint32_t misc = sb + OFF_MISC;
 
   if (threadIdx.x == 0) {
-    mbar_init(misc + MB_MMA_DONE, 1);
-    mbar_init(misc + MB_OPS_READY, 256);
-    mbar_init(misc + MB_X_FULL, 1);
-    mbar_init(misc + MB_X_FREE, 256);
-    mbar_init(misc + MB_ATTN_DONE, 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(misc + MB_W_FULL + 8 * i, 1); mbar_init(misc + MB_W_EMPTY + 8 * i, 1); }
+    const uint32_t commit_bars[] = {MB_X_FULL, MB_ATTN_DONE, MB_W_FULL, MB_W_FULL + 8, MB_W_FULL + 16, MB_W_FULL + 24,
+                                    MB_W_EMPTY, MB_W_EMPTY + 8, MB_W_EMPTY + 16, MB_W_EMPTY + 24, MB_QKV_DONE, MB_S_DONE,
+                                    MB_PV_DONE, MB_OUT_DONE, MB_F1_DONE, MB_F1_DONE + 8, MB_F2_DONE, MB_F2_DONE + 8};
+    const uint32_t warp_bars[] = {MB_X_FREE, MB_QKV_READY, MB_S_LOADED, MB_P_READY, MB_O_FREE, MB_O_FREE + 8, MB_X1_READY,
+                                  MB_F1_FREE, MB_F1_FREE + 8, MB_HID_READY, MB_X2_READY};
+    for (uint32_t b : commit_bars) mbar_init(misc + b, 1);
+    for (uint32_t b : warp_bars) mbar_init(misc + b, 8);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(misc + MISC_TMEM_PTR, 512); tmem_relinquish(); }
@@ -324,10 +417,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
 
   const int L = p.num_layers;
 
-  if (warp == 0) {
-    // ----------------------------------------------------------------------------- producer
-    if (lane == 0) {
-      uint32_t n_in = 0, n_ring = 0, n_attn = 0, n_seq = 0;   // use counters -> slot / parity
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsCtrl>();
+    if (warp == 0 && lane == 0) {
+      // ----------------------------------------------------------------------------- producer
+      uint32_t n_in = 0, n_ring = 0, n_seq = 0;
+      Phase attn_done;
       for (int64_t seq = blockIdx.x; seq < p.nseq; seq += gridDim.x, ++n_seq) {
         if (n_seq > 0) mbar_wait(misc + MB_X_FREE, (n_seq - 1) & 1);
         mbar_arrive_expect_tx(misc + MB_X_FULL, kXImageBytes);
@@ -339,12 +434,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             mbar_arrive_expect_tx(misc + MB_W_FULL, kWInSlice);
             bulk_g2s(sb + OFF_W, reinterpret_cast<const char*>(W.w_in) + g * kWInSlice, kWInSlice, misc + MB_W_FULL);
           }
-          mbar_wait(misc + MB_ATTN_DONE, n_attn & 1);   // Q/K/V images dead: the ring may overwrite them
-          ++n_attn;
-          for (int i = 0; i < 10; ++i, ++n_ring) {
+          attn_done.wait(misc + MB_ATTN_DONE);   // Q/K/V images dead: the ring may overwrite them
+          for (int i = 0; i < 10; ++i, ++n_ring) {   // ring order: Wout0 Wout1 | W1c0 W2c0 | W1c1 W2c1 | ...
             const int slot = n_ring % 3;
-            const uint32_t use = n_ring / 3;              // how many times this slot was filled before
-            if (use > 0) mbar_wait(misc + MB_W_EMPTY + 8 * (1 + slot), (use - 1) & 1);
+            const uint32_t fill = n_ring / 3;
+            if (fill > 0) mbar_wait(misc + MB_W_EMPTY + 8 * (1 + slot), (fill - 1) & 1);
             const char* src = i < 2 ? reinterpret_cast<const char*>(W.w_out) + i * kRingSlot
                                     : ((i & 1) == 0 ? reinterpret_cast<const char*>(W.w_l1) + ((i - 2) >> 1) * kRingSlot
                                                     : reinterpret_cast<const char*>(W.w_l2) + ((i - 3) >> 1) * kRingSlot);
@@ -353,147 +447,218 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ----------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      uint32_t k = 0;        // step counter (shared schedule with the compute warps)
-      uint32_t n_in = 0, n_ring = 0, n_seq = 0;
-      auto wait_ops = [&]() {
-        if (k > 0) mbar_wait(misc + MB_OPS_READY, (k - 1) & 1);
+    } else if (warp == 1 && lane == 0) {
+      // ----------------------------------------------------------------------------- MMA issuer
+      Phase x_full, x2_ready, qkv_ready, s_loaded, p_ready, x1_ready, hid_ready;
+      uint32_t n_in = 0, ring_base = 0, n_pv = 0, n_f1 = 0, n_layers_done = 0;
+      // ring entry `idx` (global index): wait until it is resident, return its address; release = commit its empty barrier
+      auto ring_wait = [&](uint32_t idx) -> uint32_t {
+        mbar_wait(misc + MB_W_FULL + 8 * (1 + idx % 3), (idx / 3) & 1);
         tc_fence_after_sync();
+        return sb + OFF_QKV + (idx % 3) * kRingSlot;
       };
-      auto end_step = [&]() { mma_commit(misc + MB_MMA_DONE); ++k; };
-      auto ring_wait = [&]() -> uint32_t {   // wait for the next ring slot to be full; returns its smem address
-        const int slot = n_ring % 3;
-        mbar_wait(misc + MB_W_FULL + 8 * (1 + slot), (n_ring / 3) & 1);
-        tc_fence_after_sync();
-        return sb + OFF_QKV + slot * kRingSlot;
-      };
-      auto ring_release = [&]() { mma_commit(misc + MB_W_EMPTY + 8 * (1 + n_ring % 3)); ++n_ring; };
+      auto ring_release = [&](uint32_t idx) { mma_commit(misc + MB_W_EMPTY + 8 * (1 + idx % 3)); };
 
-      for (int64_t seq = blockIdx.x; seq < p.nseq; seq += gridDim.x, ++n_seq) {
-        mbar_wait(misc + MB_X_FULL, n_seq & 1);
-        for (int l = 0; l < L; ++l) {
+      for (int64_t seq = blockIdx.x; seq < p.nseq; seq += gridDim.x) {
+        x_full.wait(misc + MB_X_FULL);
+        for (int l = 0; l < L; ++l, ++n_layers_done, ring_base += 10) {
+          // X and the accumulator columns [0,384) are free once the previous LayerNorm2 has finished
+          if (n_layers_done > 0) x2_ready.wait(misc + MB_X2_READY);
+          tc_fence_after_sync();
           for (int g = 0; g < 4; ++g, ++n_in) {
-            // ---- step: QKV projection of head g, all three row tiles
-            wait_ops();
+            // ---- QKV projection of head g, three row tiles (queues behind P.V(g-1, 2))
             mbar_wait(misc + MB_W_FULL, n_in & 1);
             tc_fence_after_sync();
             for (int t = 0; t < 3; ++t)
               issue_gemm_sw128(tmem, TM_QKV + t * 96, sb + OFF_X + t * 128 * 128, kXChunkBytes, sb + OFF_W, 96 * 128, 8, kIdescQkv, false);
             mma_commit(misc + MB_W_EMPTY);
-            end_step();
-            // ---- steps: S0 | S1 + PV0 | S2 + PV1 | PV2
-            for (int t = 0; t <= 3; ++t) {
-              wait_ops();
-              if (t > 0) issue_pv(tmem, sb);
-              if (t < 3) issue_scores(tmem, sb, t);
-              if (t == 3 && g == 3) mma_commit(misc + MB_ATTN_DONE);
-              end_step();
+            mma_commit(misc + MB_QKV_DONE);
+            // ---- attention of head g
+            qkv_ready.wait(misc + MB_QKV_READY);
+            tc_fence_after_sync();
+            issue_scores(tmem, sb, 0);
+            mma_commit(misc + MB_S_DONE);
+            for (int t = 0; t < 3; ++t, ++n_pv) {
+              s_loaded.wait(misc + MB_S_LOADED);      // S(t) is in registers
+              tc_fence_after_sync();
+              if (t < 2) { issue_scores(tmem, sb, t + 1); mma_commit(misc + MB_S_DONE); }
+              p_ready.wait(misc + MB_P_READY);         // P(t) is in TMEM
+              // O accumulator n_pv & 1 was last used by P.V #(n_pv - 2): its epilogue must have read it out
+              if (n_pv >= 2) mbar_wait(misc + MB_O_FREE + 8 * (n_pv & 1), ((n_pv >> 1) - 1) & 1);
+              tc_fence_after_sync();
+              issue_pv(tmem, sb, n_pv & 1);
+              mma_commit(misc + MB_PV_DONE);
+              if (g == 3 && t == 2) mma_commit(misc + MB_ATTN_DONE);
             }
           }
-          // ---- step: out_proj (A = O image, B = W_out in two ring slots, one per K-chunk)
-          wait_ops();
+          // ---- out_proj: needs every O epilogue of the layer (O image complete, P columns free)
           {
-            const uint32_t w0 = ring_wait();
+            // the epilogues of the last two P.V (#n_pv-2, #n_pv-1): O image complete, P columns free
+            mbar_wait(misc + MB_O_FREE + 8 * (n_pv & 1), ((n_pv >> 1) - 1) & 1);
+            mbar_wait(misc + MB_O_FREE + 8 * ((n_pv + 1) & 1), (((n_pv + 1) >> 1) - 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t w0 = ring_wait(ring_base + 0);
             for (int t = 0; t < 3; ++t)
-              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + t * 128 * 128, kXChunkBytes, w0, 0, 4, kIdescN128, false);
-            ring_release();
-            const uint32_t w1 = ring_wait();
+              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + t * 128 * 128, 0, w0, 0, 4, kIdescN128, false);
+            ring_release(ring_base + 0);
+            const uint32_t w1 = ring_wait(ring_base + 1);
             for (int t = 0; t < 3; ++t)
-              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + kXChunkBytes + t * 128 * 128, kXChunkBytes, w1, 0, 4, kIdescN128, true);
-            ring_release();
+              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + kXChunkBytes + t * 128 * 128, 0, w1, 0, 4, kIdescN128, true);
+            ring_release(ring_base + 1);
+            mma_commit(misc + MB_OUT_DONE);
           }
-          end_step();
-          // ---- FFN: 4 chunks of 64 hidden units; FFN2 partial products accumulate in TMEM over the chunks
-          uint32_t w1c = 0;
+          // ---- FFN: FFN1 tiles double buffered in TMEM; FFN2 partial products accumulate over the 4 hidden chunks
+          x1_ready.wait(misc + MB_X1_READY);
+          tc_fence_after_sync();
           for (int c = 0; c < 4; ++c) {
-            for (int t = 0; t < 3; ++t) {
-              wait_ops();
-              if (t == 0) w1c = ring_wait();                     // linear1 rows 64c .. 64c+63 (K = 128)
-              issue_gemm_sw128(tmem, TM_F1 + ((3 * c + t) & 1) * 64, sb + OFF_X + t * 128 * 128, kXChunkBytes, w1c, 64 * 128, 8,
-                               kIdescN64, false);
-              if (t == 2) ring_release();
-              end_step();
+            uint32_t w1c = 0;
+            for (int t = 0; t < 3; ++t, ++n_f1) {
+              const int buf = n_f1 & 1;
+              if (n_f1 >= 2) mbar_wait(misc + MB_F1_FREE + 8 * buf, ((n_f1 >> 1) - 1) & 1);
+              tc_fence_after_sync();
+              if (t == 0) w1c = ring_wait(ring_base + 2 + 2 * c);          // linear1 rows 64c .. 64c+63 (K = 128)
+              issue_gemm_sw128(tmem, TM_F1 + buf * 64, sb + OFF_X + t * 128 * 128, kXChunkBytes, w1c, 64 * 128, 8, kIdescN64, false);
+              mma_commit(misc + MB_F1_DONE + 8 * buf);
+              if (t == 2) ring_release(ring_base + 2 + 2 * c);
+              if (t == 0 && c > 0) {
+                // FFN2 partial of the previous chunk (its hidden image is complete by now or soon)
+                hid_ready.wait(misc + MB_HID_READY);
+                tc_fence_after_sync();
+                const uint32_t w2 = ring_wait(ring_base + 3 + 2 * (c - 1));
+                for (int tt = 0; tt < 3; ++tt)
+                  issue_gemm_sw128(tmem, TM_OUT + tt * 128, sb + OFF_O + ((c - 1) & 1) * kHidBytes + tt * 128 * 128, 0, w2, 0, 4,
+                                   kIdescN128, c - 1 > 0);
+                ring_release(ring_base + 3 + 2 * (c - 1));
+                mma_commit(misc + MB_F2_DONE + 8 * ((c - 1) & 1));
+              }
             }
-            // ---- step: FFN2 partial, hidden chunk c (K = 64) x linear2 columns 64c .. 64c+63
-            wait_ops();
-            {
-              const uint32_t w2c = ring_wait();
-              for (int t = 0; t < 3; ++t)
-                issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + (c & 1) * kHidBytes + t * 128 * 128, 0, w2c, 0, 4, kIdescN128, c > 0);
-              ring_release();
-            }
-            end_step();
+          }
+          hid_ready.wait(misc + MB_HID_READY);
+          tc_fence_after_sync();
+          {
+            const uint32_t w2 = ring_wait(ring_base + 9);
+            for (int tt = 0; tt < 3; ++tt)
+              issue_gemm_sw128(tmem, TM_OUT + tt * 128, sb + OFF_O + kHidBytes + tt * 128 * 128, 0, w2, 0, 4, kIdescN128, true);
+            ring_release(ring_base + 9);
+            mma_commit(misc + MB_F2_DONE + 8);
           }
         }
       }
     }
   } else {
     // ----------------------------------------------------------------------------- compute warps
-    const int q = warp & 3, half = (warp - 2) >> 2;
-    const bool tile2_active = (q == 0);   // third row tile: only rows 256..287 exist
-    uint32_t k = 0;
-    auto wait_mma = [&]() {
-      mbar_wait(misc + MB_MMA_DONE, k & 1);
-      tc_fence_after_sync();
-    };
-    auto end_step = [&]() {
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(misc + MB_OPS_READY);
-      ++k;
-    };
+    setmaxnreg_inc<kRegsCompute>();
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int rt = q * 32 + lane;                // row inside a 128-row tile
+    const bool tile2_active = (q == 0);          // third row tile: only rows 256..287 exist
+    Phase x_full, qkv_done, s_done, pv_done, out_done;
+    uint32_t n_pv = 0, n_f1 = 0;
+    const uint32_t xmax_mine = misc + MISC_XMAX + (half * 128 + rt) * 4, xmax_other = misc + MISC_XMAX + ((half ^ 1) * 128 + rt) * 4;
+    const uint32_t xsum_mine = misc + MISC_XSUM + (half * 128 + rt) * 4, xsum_other = misc + MISC_XSUM + ((half ^ 1) * 128 + rt) * 4;
+
+#pragma unroll 1
     for (int64_t seq = blockIdx.x; seq < p.nseq; seq += gridDim.x) {
       float* h_seq = p.h_out + seq * (int64_t)kS * kD;
+      x_full.wait(misc + MB_X_FULL);   // the residual image is read with generic loads by the LayerNorm epilogues
+#pragma unroll 1
       for (int l = 0; l < L; ++l) {
+#pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          wait_mma();
-          if (half == 0) {
-            epi_qkv(tmem, sb, l, g, 0, q, lane);
-            if (tile2_active) epi_qkv(tmem, sb, l, g, 2, q, lane);
-          } else {
-            epi_qkv(tmem, sb, l, g, 1, q, lane);
-          }
-          end_step();
-          for (int t = 0; t <= 3; ++t) {
-            wait_mma();
-            if (t > 0 && (t - 1 < 2 || tile2_active)) epi_o(tmem, sb, g, t - 1, q, half, lane);
-            if (t < 3) epi_softmax(tmem, sb, t < 2 || tile2_active, q, half, lane);
-            end_step();
-          }
-        }
-        wait_mma();
-        if (half == 0) {
-          epi_ln(tmem, sb, l, 1, 0, q, lane, nullptr);
-          if (tile2_active) epi_ln(tmem, sb, l, 1, 2, q, lane, nullptr);
-        } else {
-          epi_ln(tmem, sb, l, 1, 1, q, lane, nullptr);
-        }
-        end_step();
-        for (int c = 0; c < 4; ++c) {
-          for (int t = 0; t < 3; ++t) {
-            wait_mma();
-            if (t < 2 || tile2_active) epi_act(tmem, sb, l, c, t, (3 * c + t) & 1, p.activation, q, half, lane);
-            end_step();
-          }
-          wait_mma();
-          if (c == 3) {
-            float* ho = (l == L - 1) ? h_seq : nullptr;
-            if (half == 0) {
-              epi_ln(tmem, sb, l, 2, 0, q, lane, ho);
-              if (tile2_active) epi_ln(tmem, sb, l, 2, 2, q, lane, ho);
+          // ---- QKV epilogue of head g (warpgroup 0: row tiles 0 and 2, warpgroup 1: row tile 1)
+          qkv_done.wait(misc + MB_QKV_DONE);
+          tc_fence_after_sync();
+#pragma unroll 1
+          for (int t = 0; t < 3; ++t)
+            if (t < 2 || tile2_active) epi_qkv(tmem, sb, l, g, t, q, half, lane);
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          warp_arrive(misc + MB_QKV_READY, lane);
+          // ---- softmax tiles; the O epilogue of tile t-1 runs after P(t) has been handed to the tensor core
+          float inv_prev = 0.f;
+#pragma unroll 1
+          for (int t = 0; t < 4; ++t) {
+            const bool active = t < 2 || tile2_active;
+            float sum = 0.f;
+            if (t < 3) {
+              float v[144];
+              float m = 0.f;
+              s_done.wait(misc + MB_S_DONE);
+              tc_fence_after_sync();
+              if (active) {
+                m = softmax_load(tmem, q, half, v);
+                st_shared_f32(xmax_mine, m);
+              }
+              tc_fence_before_sync();
+              warp_arrive(misc + MB_S_LOADED, lane);
+              named_bar_sync(1 + q, 64);                                   // exchange the half-row maxima
+              if (active) {
+                m = fmaxf(m, ld_shared_f32(xmax_other));
+                sum = softmax_exp(v, m);
+              }
+              if (t > 0) { pv_done.wait(misc + MB_PV_DONE); tc_fence_after_sync(); }   // P.V(t-1) has consumed P
+              if (active) {
+                softmax_store(tmem, q, half, v);
+                st_shared_f32(xsum_mine, sum);
+              }
+              tc_fence_before_sync();
+              warp_arrive(misc + MB_P_READY, lane);
             } else {
-              epi_ln(tmem, sb, l, 2, 1, q, lane, ho);
+              pv_done.wait(misc + MB_PV_DONE);
+              tc_fence_after_sync();
             }
-            if (l == L - 1) {   // the X image may now be replaced (async proxy) by the next sequence
+            if (t > 0) {
+              if (t - 1 < 2 || tile2_active) epi_o(tmem, sb, g, t - 1, (n_pv - 1) & 1, inv_prev, q, half, lane);
+              tc_fence_before_sync();
               fence_proxy_async_smem();
-              mbar_arrive(misc + MB_X_FREE);
+              warp_arrive(misc + MB_O_FREE + 8 * ((n_pv - 1) & 1), lane);
+            }
+            if (t < 3) {
+              named_bar_sync(1 + q, 64);                                   // exchange the half-row sums
+              inv_prev = active ? rcp_approx(sum + ld_shared_f32(xsum_other)) : 0.f;
+              ++n_pv;
             }
           }
-          end_step();
         }
+        // ---- out_proj epilogue: + bias + residual -> LayerNorm1 -> X
+        out_done.wait(misc + MB_OUT_DONE);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int t = 0; t < 3; ++t)
+          if (t < 2 || tile2_active) epi_ln(tmem, sb, l, 1, t, q, half, lane, xmax_mine, xmax_other, nullptr);
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        warp_arrive(misc + MB_X1_READY, lane);
+        // ---- FFN1 epilogues: bias + GELU -> hidden chunk images
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (c >= 2) mbar_wait(misc + MB_F2_DONE + 8 * (c & 1), 0);   // FFN2(c-2) has consumed hidden buffer c & 1
+#pragma unroll 1
+          for (int t = 0; t < 3; ++t, ++n_f1) {
+            const int buf = n_f1 & 1;
+            const bool active = t < 2 || tile2_active;
+            float f[32];
+            mbar_wait(misc + MB_F1_DONE + 8 * buf, (n_f1 >> 1) & 1);
+            tc_fence_after_sync();
+            if (active) act_load(tmem, l, c, buf, q, half, f);
+            tc_fence_before_sync();
+            warp_arrive(misc + MB_F1_FREE + 8 * buf, lane);
+            if (active) act_store(sb, c, t, p.activation, q, half, lane, f);
+          }
+          fence_proxy_async_smem();
+          warp_arrive(misc + MB_HID_READY, lane);
+        }
+        // ---- linear2 epilogue: + bias + residual -> LayerNorm2 -> X (+ fp32 result after the last layer)
+        mbar_wait(misc + MB_F2_DONE, 1);        // FFN2(2) and FFN2(3): second completion of each barrier in this layer
+        mbar_wait(misc + MB_F2_DONE + 8, 1);
+        tc_fence_after_sync();
+        float* ho = (l == L - 1) ? h_seq : nullptr;
+#pragma unroll 1
+        for (int t = 0; t < 3; ++t)
+          if (t < 2 || tile2_active) epi_ln(tmem, sb, l, 2, t, q, half, lane, xmax_mine, xmax_other, ho);
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        if (l == L - 1) warp_arrive(misc + MB_X_FREE, lane);
+        warp_arrive(misc + MB_X2_READY, lane);
       }
     }
   }
@@ -632,7 +797,8 @@ size_t tc_workspace_bytes(int64_t bc) {
 
 bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack& head, int activation, int sm_count,
                       const float2* pilots, const float* snr, const float* ds, const float* dop, float2* out,
-                      int64_t nsamples, void* workspace, cudaStream_t st) {
+                      int64_t nsamples, void* workspace, cudaStream_t st, TcProfileHook hook) {
+  auto mark = [&]() { if (hook.mark) hook.mark(hook.ctx, st); };
   if (w.num_layers > kTcMaxLayers) {
     set_error("AFT_BF16 path supports at most %d encoder layers (got %d)", kTcMaxLayers, w.num_layers);
     return false;
@@ -642,6 +808,7 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   float* enh = reinterpret_cast<float*>(ws);
   char* ximg = ws + align_up_sz(nseq * kPix * sizeof(float), 1024);
   float* hout = reinterpret_cast<float*>(ximg + align_up_sz(nseq * (size_t)kXImageBytes, 1024));
+  mark();
   if (!launch_frontend(front, pilots, snr, ds, dop, enh, nullptr, reinterpret_cast<__nv_bfloat16*>(ximg), nsamples, st)) return false;
   // per-layer epilogue vectors -> constant bank (device-to-device, stream ordered; 5.5 KB per layer)
   if (cudaMemcpyToSymbolAsync(c_vec, w.layers[0].b_in, (size_t)w.num_layers * kVecPerLayer * sizeof(float), 0,
@@ -661,10 +828,14 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   ep.activation = activation;
   ep.nseq = nseq;
   const unsigned grid = (unsigned)(nseq < sm_count ? nseq : sm_count);
+  mark();
   encoder_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(ep);
   count_launch();
   if (!check_launch("encoder_kernel")) return false;
-  return launch_head(head, hout, enh, out, nsamples, st);
+  mark();
+  const bool ok = launch_head(head, hout, enh, out, nsamples, st);
+  mark();
+  return ok;
 }
 
 // =============================================================================================
@@ -709,53 +880,67 @@ __global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const char* a_img
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-// which = 1: one attention row tile with the production helpers: S = Q K^T (SW64), softmax -> P (TMEM), O = P V (MN-major)
+// which = 1, 2: one attention row tile with the production helpers: S = Q K^T (SW64), softmax -> P (TMEM), O = P V (MN-major)
 __global__ void __launch_bounds__(kTcThreads, 1) selftest_attn_kernel(const char* qkv_img, float* s_out, float* o_out, int tile) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t misc = sb + OFF_MISC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) { mbar_init(misc + MB_MMA_DONE, 1); mbar_init(misc + MB_OPS_READY, 256); mbar_init(misc + MB_X_FULL, 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) {
+    mbar_init(misc + MB_X_FULL, 1); mbar_init(misc + MB_S_DONE, 1); mbar_init(misc + MB_PV_DONE, 1);
+    mbar_init(misc + MB_P_READY, 8);
+    fence_mbar_init();
+  }
   if (warp == 1) { tmem_alloc(misc + MISC_TMEM_PTR, 512); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(misc + MISC_TMEM_PTR));
-  if (warp == 1 && lane == 0) {
-    mbar_arrive_expect_tx(misc + MB_X_FULL, 3 * kQkvPart);
-    bulk_g2s(sb + OFF_QKV, qkv_img, 3 * kQkvPart, misc + MB_X_FULL);
-    mbar_wait(misc + MB_X_FULL, 0);
-    tc_fence_after_sync();
-    issue_scores(tmem, sb, tile);
-    mma_commit(misc + MB_MMA_DONE);
-    mbar_wait(misc + MB_OPS_READY, 0);
-    tc_fence_after_sync();
-    issue_pv(tmem, sb);
-    mma_commit(misc + MB_MMA_DONE);
-  } else if (warp >= 2) {
-    const int q = warp & 3, half = (warp - 2) >> 2;
-    const bool active = tile < 2 || q == 0;
-    mbar_wait(misc + MB_MMA_DONE, 0);
-    tc_fence_after_sync();
-    if (active) {   // dump raw scores
-      for (int i = 0; i < 9; ++i) {
-        uint32_t v[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_S + half * 144 + i * 16, v);
-        tmem_wait_ld();
-        for (int j = 0; j < 16; ++j) s_out[(q * 32 + lane) * 288 + half * 144 + i * 16 + j] = __uint_as_float(v[j]);
-      }
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsCtrl>();
+    if (warp == 1 && lane == 0) {
+      mbar_arrive_expect_tx(misc + MB_X_FULL, 3 * kQkvPart);
+      bulk_g2s(sb + OFF_QKV, qkv_img, 3 * kQkvPart, misc + MB_X_FULL);
+      mbar_wait(misc + MB_X_FULL, 0);
+      tc_fence_after_sync();
+      issue_scores(tmem, sb, tile);
+      mma_commit(misc + MB_S_DONE);
+      mbar_wait(misc + MB_P_READY, 0);
+      tc_fence_after_sync();
+      issue_pv(tmem, sb, 1);
+      mma_commit(misc + MB_PV_DONE);
     }
-    epi_softmax(tmem, sb, active, q, half, lane);
+  } else {
+    setmaxnreg_inc<kRegsCompute>();
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int rt = q * 32 + lane;
+    const bool active = tile < 2 || q == 0;
+    mbar_wait(misc + MB_S_DONE, 0);
+    tc_fence_after_sync();
+    float v[144];
+    float m = 0.f, sum = 0.f;
+    if (active) {
+      m = softmax_load(tmem, q, half, v);
+      for (int j = 0; j < 144; ++j) s_out[rt * 288 + half * 144 + j] = v[j];   // raw scores (padding keys read -inf)
+      st_shared_f32(misc + MISC_XMAX + (half * 128 + rt) * 4, m);
+    }
+    named_bar_sync(1 + q, 64);
+    if (active) {
+      m = fmaxf(m, ld_shared_f32(misc + MISC_XMAX + ((half ^ 1) * 128 + rt) * 4));
+      sum = softmax_exp(v, m);
+      softmax_store(tmem, q, half, v);
+      st_shared_f32(misc + MISC_XSUM + (half * 128 + rt) * 4, sum);
+    }
     tc_fence_before_sync();
-    mbar_arrive(misc + MB_OPS_READY);
-    mbar_wait(misc + MB_MMA_DONE, 1);
+    warp_arrive(misc + MB_P_READY, lane);
+    named_bar_sync(1 + q, 64);
+    mbar_wait(misc + MB_PV_DONE, 0);
     tc_fence_after_sync();
     if (active) {
-      const int rt = q * 32 + lane;
-      const float l = ld_shared_f32(misc + MISC_XSUM + rt * 4) + ld_shared_f32(misc + MISC_XSUM + (128 + rt) * 4);
+      const float l = sum + ld_shared_f32(misc + MISC_XSUM + ((half ^ 1) * 128 + rt) * 4);
       uint32_t a[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_O + half * 16, a);
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_O + 32 + half * 16, a);
       tmem_wait_ld();
       for (int j = 0; j < 16; ++j) o_out[rt * 32 + half * 16 + j] = __uint_as_float(a[j]) / l;
     }
@@ -790,6 +975,34 @@ struct Lcg {
 
 bool tc_selftest(int which, double* max_err, cudaStream_t st) {
   *max_err = -1.0;
+  if (which >= 100) {
+    // diagnostics: 100 = arm the wait-timeout channel (mapped host memory), 101 = print and clear its records
+    static unsigned long long* host_buf = nullptr;
+    if (which == 100) {
+      if (!host_buf) {
+        if (cudaHostAlloc(&host_buf, 64 * 16 * 8, cudaHostAllocMapped) != cudaSuccess) { set_error("diag: cudaHostAlloc failed"); return false; }
+        memset(host_buf, 0, 64 * 16 * 8);
+        unsigned long long* dev = nullptr;
+        cudaHostGetDevicePointer(&dev, host_buf, 0);
+        cudaMemcpyToSymbol(g_wait_diag, &dev, sizeof(dev));
+      }
+      *max_err = 0.0;
+      return true;
+    }
+    int n = 0;
+    if (host_buf)
+      for (int i = 0; i < 64 * 16; ++i)
+        if (host_buf[i] >> 63) {
+          const unsigned long long r = host_buf[i];
+          if (n < 48)
+            fprintf(stderr, "aft wait-timeout: block %llu thread %llu (warp %llu) parity %llu barrier@misc+%llu\n", (r >> 40) & 0x7FFFFF,
+                    (r >> 24) & 0xFFFF, ((r >> 24) & 0xFFFF) >> 5, (r >> 16) & 0xFF, (r & 0xFFFF) & 1023);
+          host_buf[i] = 0;
+          ++n;
+        }
+    *max_err = n;
+    return true;
+  }
   Lcg rng{12345u + (uint64_t)which};
   if (which == 0) {
     std::vector<float> A(288 * 128), B(96 * 128);

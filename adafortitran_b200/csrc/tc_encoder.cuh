@@ -29,9 +29,13 @@ bool tc_weights_alloc(TcWeights& w, int num_layers);
 void tc_weights_free(TcWeights& w);
 bool tc_weights_pack(TcWeights& w, const std::vector<LayerPackF32>& src, cudaStream_t st);
 size_t tc_workspace_bytes(int64_t chunk_samples);
+struct TcProfileHook {
+  void (*mark)(void* ctx, cudaStream_t st);   // nullptr when profiling is off
+  void* ctx;
+};
 bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack& head, int activation, int sm_count,
                       const float2* pilots, const float* snr, const float* ds, const float* dop, float2* out,
-                      int64_t nsamples, void* workspace, cudaStream_t st);
+                      int64_t nsamples, void* workspace, cudaStream_t st, TcProfileHook hook);
 bool tc_selftest(int which, double* max_err, cudaStream_t st);
 
 }  // namespace aft

@@ -50,14 +50,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as a trap (reported as a CUDA error), never as a hung GPU.
+// Diagnostics channel: device pointer to mapped host memory (survives a trapped kernel), set by the host.
+// Record layout: slot [block % 64][warp % 16] = 1<<63 | block<<40 | thread<<24 | parity<<16 | (barrier smem address & 0xFFFF).
+__device__ unsigned long long* g_wait_diag = nullptr;
+
+// Bounded spin: a protocol bug must surface as a trap (reported as a CUDA error), never as a hung GPU.  The first
+// threads to time out leave a record and keep spinning a little so that every stuck role gets to report.
+__device__ __noinline__ void mbar_wait_timeout(uint32_t bar, uint32_t parity) {
+  if (g_wait_diag != nullptr)
+    g_wait_diag[(blockIdx.x & 63) * 16 + ((threadIdx.x >> 5) & 15)] =
+        (1ull << 63) | ((unsigned long long)blockIdx.x << 40) | ((unsigned long long)threadIdx.x << 24) |
+        ((unsigned long long)parity << 16) | (bar & 0xFFFFu);
+  __threadfence_system();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 20000000u) {
-      printf("aft: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
+    ++spins;
+    if (spins == 4000000u) mbar_wait_timeout(bar, parity);
+    if (spins > 6000000u) __trap();
   }
 }
 

@@ -140,6 +140,13 @@ AFT_API int aft_error_sums(const void* est, const void* truth, int64_t count, do
 /* Number of kernel launches issued by this library on the calling process since load (for bench.py). */
 AFT_API int64_t aft_launch_count(void);
 
+/* Stage timing for bench.py's roofline: when enabled, aft_forward brackets the frontend, encoder and head
+ * launches of every chunk with CUDA events on the launch stream.  aft_profile_read synchronises on the recorded
+ * events, returns the accumulated milliseconds per stage (ms[0..2] = frontend, encoder, head) and the number of
+ * launches per stage, and resets the accumulators.  fp32 path: "encoder" covers its GEMM + attention kernels. */
+AFT_API int aft_profile_enable(AftHandle* h, int enable);
+AFT_API int aft_profile_read(AftHandle* h, double* ms, int64_t* launches);
+
 /* Device-side self tests of the tcgen05 building blocks against SIMT code (returns max abs error in
  * *max_err; used by tests/ to localise failures).  which: 0 = UMMA GEMM tile, 1 = attention tile. */
 AFT_API int aft_selftest(int which, double* max_err, void* stream);

@@ -28,8 +28,26 @@ def forward_check(kind="ada", B=8):
     print(json.dumps({"bf16_forward": kind, "B": B, "normwise": O.normwise_err(y, ref), "rel_db": O.rel_err_db(y, ref),
                       "finite": bool(np.isfinite(y.view(np.float32)).all())}), flush=True)
 
+def arm_diag():
+    torch.zeros(1, device="cuda")
+    err = C.c_double(-1)
+    _capi.lib().aft_selftest(100, C.byref(err), None)
+
+def dump_diag():
+    err = C.c_double(-1)
+    _capi.lib().aft_selftest(101, C.byref(err), None)
+    print("diag records:", err.value, flush=True)
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "diag":
+        arm_diag()
+        try:
+            forward_check("forti", 2)
+        except Exception as e:
+            print("forward failed:", str(e)[:200])
+        dump_diag()
+        sys.exit(0)
     if what in ("all", "self"): selftests()
     if what in ("all", "fwd"):
         forward_check("forti", 2); forward_check("forti", 160); forward_check("ada", 8)

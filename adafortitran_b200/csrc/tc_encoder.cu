@@ -6,9 +6,9 @@
 // Per sequence the only HBM traffic is the 72 KB input image and the 140 KB fp32 result; weights (256 KB bf16
 // per layer) are streamed from L2 by 1-D bulk copies (cp.async.bulk) into a small ring.
 //
-//   warpgroup 0 : warp 0 = producer (bulk copies + expect_tx), warp 1 = MMA issuer (one thread issues every
-//                 tcgen05.mma, owns the TMEM allocation); warps 2,3 idle.  Registers shrunk with setmaxnreg.
-//   warpgroups 1,2 : 8 compute warps -- TMEM -> registers epilogues (bias, softmax, 1/l, residual + LayerNorm,
+//   warpgroup 2 : warp 10 = producer (bulk copies + expect_tx), warp 11 = MMA issuer (one thread issues every
+//                 tcgen05.mma, owns the TMEM allocation); warps 8,9 idle.  Registers shrunk with setmaxnreg.
+//   warpgroups 0,1 : 8 compute warps -- TMEM -> registers epilogues (bias, softmax, 1/l, residual + LayerNorm,
 //                 GELU), writing the next operand image (bf16) to shared memory / P to TMEM.  Registers grown
 //                 to 224 so a thread can hold a 144-wide score row or a 128-wide LayerNorm row.
 //
@@ -32,6 +32,7 @@
 //   QKV accumulators alias S; out_proj / FFN2 accumulators [0,384); FFN1 accumulators [384,448) [448,512).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -45,7 +46,8 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kTcThreads = 384;      // 3 warpgroups: [producer, MMA, idle, idle] + 2 x 4 compute warps
+constexpr int kTcThreads = 384;      // 3 warpgroups: 2 x 4 compute warps + [idle, idle, producer, MMA]
+constexpr int kProducerWarp = 10, kMmaWarp = 11;   // highest warp ids: the issue arbiter favours them over the compute warps
 constexpr int kRegsCtrl = 56;        // setmaxnreg budget of warpgroup 0
 constexpr int kRegsCompute = 224;    // setmaxnreg budget of the compute warpgroups  (128*56 + 256*224 = 64512 <= 65536)
 constexpr int kTcMaxLayers = 8;
@@ -167,29 +169,35 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 // D (N cols at d_col) (+)= A(image with 128-B rows)[128 rows at a_base] . B(image at b_base)^T ; K = 16 * ksteps
 __device__ __forceinline__ void issue_gemm_sw128(uint32_t tmem, uint32_t d_col, uint32_t a_base, uint32_t a_chunk_bytes,
                                                  uint32_t b_base, uint32_t b_chunk_bytes, int ksteps, uint32_t idesc,
-                                                 bool accumulate_first) {
+                                                 bool accumulate_first, bool el = true) {
+  // descriptor = (hi: SBO | version | swizzle, constant) : (lo: LBO | start address >> 4); the K step only moves `lo`
+  constexpr uint32_t kHi = (uint32_t)(desc_k_sw128_const() >> 32);
+  const uint32_t a_lo = (uint32_t)desc_k_sw128_const() | ((a_base >> 4) & 0x3FFF);
+  const uint32_t b_lo = (uint32_t)desc_k_sw128_const() | ((b_base >> 4) & 0x3FFF);
+  const uint32_t a_chunk = a_chunk_bytes >> 4, b_chunk = b_chunk_bytes >> 4;
+#pragma unroll 4
   for (int ks = 0; ks < ksteps; ++ks) {
-    const uint32_t a = a_base + (ks >> 2) * a_chunk_bytes + (ks & 3) * 32;
-    const uint32_t b = b_base + (ks >> 2) * b_chunk_bytes + (ks & 3) * 32;
-    mma_ss(tmem + d_col, desc_k_sw128(a), desc_k_sw128(b), idesc, accumulate_first || ks > 0);
+    const uint32_t a = a_lo + (ks >> 2) * a_chunk + (ks & 3) * 2;
+    const uint32_t b = b_lo + (ks >> 2) * b_chunk + (ks & 3) * 2;
+    mma_ss(tmem + d_col, ((uint64_t)kHi << 32) | a, ((uint64_t)kHi << 32) | b, idesc, accumulate_first || ks > 0, el);
   }
 }
 // S[tile t] = Q_g[tile t] . K_g^T   (two N = 144 halves, K = 32)
-__device__ __forceinline__ void issue_scores(uint32_t tmem, uint32_t sb, int t) {
+__device__ __forceinline__ void issue_scores(uint32_t tmem, uint32_t sb, int t, bool el = true) {
   const uint32_t q = sb + OFF_QKV + t * 128 * 64;
   const uint32_t k = sb + OFF_QKV + kQkvPart;
 #pragma unroll
   for (int nh = 0; nh < 2; ++nh)
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
-      mma_ss(tmem + TM_S + nh * 144, desc_k_sw64(q + ks * 32), desc_k_sw64(k + nh * 144 * 64 + ks * 32), kIdescS, ks > 0);
+      mma_ss(tmem + TM_S + nh * 144, desc_k_sw64(q + ks * 32), desc_k_sw64(k + nh * 144 * 64 + ks * 32), kIdescS, ks > 0, el);
 }
 // O_acc[buf] = P (TMEM, bf16 pairs) . V_g   (K = 288 keys = 18 steps, N = 32)
-__device__ __forceinline__ void issue_pv(uint32_t tmem, uint32_t sb, int obuf) {
+__device__ __forceinline__ void issue_pv(uint32_t tmem, uint32_t sb, int obuf, bool el = true) {
   const uint32_t v = sb + OFF_QKV + 2 * kQkvPart;
-#pragma unroll 1
+#pragma unroll 6
   for (int ks = 0; ks < 18; ++ks)
-    mma_ts(tmem + TM_O + obuf * 32, tmem + TM_P + ks * 8, desc_mn_sw64(v + ks * 1024), kIdescPV, ks > 0);
+    mma_ts(tmem + TM_O + obuf * 32, tmem + TM_P + ks * 8, desc_mn_sw64(v + ks * 1024), kIdescPV, ks > 0, el);
 }
 
 // =============================================================================================
@@ -201,13 +209,15 @@ __device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, int l, int g
   const int r = t * 128 + q * 32 + lane;
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + t * 96 + half * 48;
   const int sw = (r >> 1) & 3;
+  uint32_t acc[48];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tmem_ld16(taddr + i * 16, reinterpret_cast<uint32_t(&)[16]>(acc[i * 16]));
+  tmem_wait_ld();
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int col = half * 48 + i * 16;        // column inside [q | k | v], a multiple of 16
     const int part = col >> 5, c0 = col & 31;  // which matrix, first column inside its 32
-    uint32_t a[16];
-    tmem_ld16(taddr + i * 16, a);
-    tmem_wait_ld();
+    const uint32_t* a = acc + i * 16;
     const float* bias = c_vec + l * kVecPerLayer + part * 128 + g * 32 + c0;
     uint32_t pk[8];
 #pragma unroll
@@ -223,14 +233,10 @@ __device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, int l, int g
 // (1) load this thread's 144 score columns (half 1: 136 valid) and the half-row maximum
 __device__ __forceinline__ float softmax_load(uint32_t tmem, int q, int half, float (&v)[144]) {
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+  uint32_t(&x)[144] = reinterpret_cast<uint32_t(&)[144]>(v);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    uint32_t x[16];
-    tmem_ld16(lane_addr + TM_S + half * 144 + i * 16, x);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[i * 16 + j] = __uint_as_float(x[j]);
-  }
+  for (int i = 0; i < 9; ++i) tmem_ld16(lane_addr + TM_S + half * 144 + i * 16, reinterpret_cast<uint32_t(&)[16]>(x[i * 16]));
+  tmem_wait_ld();
   if (half == 1) {
 #pragma unroll
     for (int j = kS - 144; j < 144; ++j) v[j] = -INFINITY;   // keys 280..287 are padding
@@ -293,11 +299,13 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, int l, int wh
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_OUT + t * 128 + half * 64;
   const uint32_t xrow = sb + OFF_X + half * kXChunkBytes + r * 128;
   float v[64];
+  uint32_t acc[64];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tmem_ld16(taddr + i * 16, reinterpret_cast<uint32_t(&)[16]>(acc[i * 16]));
+  tmem_wait_ld();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    uint32_t a[16];
-    tmem_ld16(taddr + i * 16, a);
-    tmem_wait_ld();
+    const uint32_t* a = acc + i * 16;
 #pragma unroll
     for (int hu = 0; hu < 2; ++hu) {
       const int u = i * 2 + hu;   // 16-byte unit = 8 columns
@@ -384,7 +392,19 @@ struct EncParams {
   int num_layers;
   int activation;
   int64_t nseq;
+  unsigned long long* timeline;   // diagnostics (device memory): (id << 48 | clock) records, 0-terminated; nullptr = off
 };
+
+// timeline events are recorded by block 0 only, for its second sequence, second layer (steady state): plain stores
+// into device memory, MMA thread in slots [0,500), compute thread 0 in slots [500,1000)
+__device__ __forceinline__ void tl_event(const EncParams& p, bool on, uint32_t id, uint32_t& n) {
+  if (on) {
+    unsigned long long* base = p.timeline + (id >= 200 ? 500 : 0);
+    const unsigned long long t = clock64();
+    ++n;                                        // register-resident count; slot 0 of each half mirrors it
+    if (n < 500) { base[n] = ((unsigned long long)id << 48) | (t & 0xFFFFFFFFFFFFull); base[0] = n; }
+  }
+}
 
 // use counter of an mbarrier on one side of the protocol: wait()/done() walk the phases in order
 struct Phase {
@@ -408,7 +428,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
     for (uint32_t b : warp_bars) mbar_init(misc + b, 8);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(misc + MISC_TMEM_PTR, 512); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc(misc + MISC_TMEM_PTR, 512); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -417,28 +437,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
 
   const int L = p.num_layers;
 
-  if (warp < 4) {
+  if (warp >= 8) {
     setmaxnreg_dec<kRegsCtrl>();
-    if (warp == 0 && lane == 0) {
+    if (warp == kProducerWarp && lane == 0) {
       // ----------------------------------------------------------------------------- producer
-      uint32_t n_in = 0, n_ring = 0, n_seq = 0;
-      Phase attn_done;
+      uint32_t n_in = 0, n_ring = 0, n_seq = 0, n_attn = 0;
       for (int64_t seq = blockIdx.x; seq < p.nseq; seq += gridDim.x, ++n_seq) {
-        if (n_seq > 0) mbar_wait(misc + MB_X_FREE, (n_seq - 1) & 1);
+        if (n_seq > 0) mbar_wait_relaxed(misc + MB_X_FREE, (n_seq - 1) & 1);
         mbar_arrive_expect_tx(misc + MB_X_FULL, kXImageBytes);
         bulk_g2s(sb + OFF_X, p.x_images + seq * (int64_t)kXImageBytes, kXImageBytes, misc + MB_X_FULL);
         for (int l = 0; l < L; ++l) {
           const TcLayer& W = p.layers[l];
           for (int g = 0; g < 4; ++g, ++n_in) {
-            if (n_in > 0) mbar_wait(misc + MB_W_EMPTY, (n_in - 1) & 1);
+            if (n_in > 0) mbar_wait_relaxed(misc + MB_W_EMPTY, (n_in - 1) & 1);
             mbar_arrive_expect_tx(misc + MB_W_FULL, kWInSlice);
             bulk_g2s(sb + OFF_W, reinterpret_cast<const char*>(W.w_in) + g * kWInSlice, kWInSlice, misc + MB_W_FULL);
           }
-          attn_done.wait(misc + MB_ATTN_DONE);   // Q/K/V images dead: the ring may overwrite them
+          mbar_wait_relaxed(misc + MB_ATTN_DONE, n_attn & 1);   // Q/K/V images dead: the ring may overwrite them
+          ++n_attn;
           for (int i = 0; i < 10; ++i, ++n_ring) {   // ring order: Wout0 Wout1 | W1c0 W2c0 | W1c1 W2c1 | ...
             const int slot = n_ring % 3;
             const uint32_t fill = n_ring / 3;
-            if (fill > 0) mbar_wait(misc + MB_W_EMPTY + 8 * (1 + slot), (fill - 1) & 1);
+            if (fill > 0) mbar_wait_relaxed(misc + MB_W_EMPTY + 8 * (1 + slot), (fill - 1) & 1);
             const char* src = i < 2 ? reinterpret_cast<const char*>(W.w_out) + i * kRingSlot
                                     : ((i & 1) == 0 ? reinterpret_cast<const char*>(W.w_l1) + ((i - 2) >> 1) * kRingSlot
                                                     : reinterpret_cast<const char*>(W.w_l2) + ((i - 3) >> 1) * kRingSlot);
@@ -447,21 +467,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == kMmaWarp) {
       // ----------------------------------------------------------------------------- MMA issuer
+      // The whole warp runs the schedule converged (all lanes poll the barriers, addresses stay warp-uniform and live in
+      // uniform registers); only the tcgen05.mma / tcgen05.commit instructions are predicated on the elected lane.
+      const bool el = elect_one();
       Phase x_full, x2_ready, qkv_ready, s_loaded, p_ready, x1_ready, hid_ready;
-      uint32_t n_in = 0, ring_base = 0, n_pv = 0, n_f1 = 0, n_layers_done = 0;
+      uint32_t n_in = 0, ring_base = 0, n_pv = 0, n_f1 = 0, n_layers_done = 0, tl_n = 0;
       // ring entry `idx` (global index): wait until it is resident, return its address; release = commit its empty barrier
       auto ring_wait = [&](uint32_t idx) -> uint32_t {
         mbar_wait(misc + MB_W_FULL + 8 * (1 + idx % 3), (idx / 3) & 1);
         tc_fence_after_sync();
         return sb + OFF_QKV + (idx % 3) * kRingSlot;
       };
-      auto ring_release = [&](uint32_t idx) { mma_commit(misc + MB_W_EMPTY + 8 * (1 + idx % 3)); };
+      auto ring_release = [&](uint32_t idx) { mma_commit(misc + MB_W_EMPTY + 8 * (1 + idx % 3), el); };
 
       for (int64_t seq = blockIdx.x; seq < p.nseq; seq += gridDim.x) {
         x_full.wait(misc + MB_X_FULL);
         for (int l = 0; l < L; ++l, ++n_layers_done, ring_base += 10) {
+          const bool tl = p.timeline != nullptr && blockIdx.x == 0 && seq == (int64_t)gridDim.x && l == 1 && lane == 0;
           // X and the accumulator columns [0,384) are free once the previous LayerNorm2 has finished
           if (n_layers_done > 0) x2_ready.wait(misc + MB_X2_READY);
           tc_fence_after_sync();
@@ -469,26 +493,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             // ---- QKV projection of head g, three row tiles (queues behind P.V(g-1, 2))
             mbar_wait(misc + MB_W_FULL, n_in & 1);
             tc_fence_after_sync();
+            tl_event(p, tl, 100 + g, tl_n);   // QKV(g) issue start
             for (int t = 0; t < 3; ++t)
-              issue_gemm_sw128(tmem, TM_QKV + t * 96, sb + OFF_X + t * 128 * 128, kXChunkBytes, sb + OFF_W, 96 * 128, 8, kIdescQkv, false);
-            mma_commit(misc + MB_W_EMPTY);
-            mma_commit(misc + MB_QKV_DONE);
+              issue_gemm_sw128(tmem, TM_QKV + t * 96, sb + OFF_X + t * 128 * 128, kXChunkBytes, sb + OFF_W, 96 * 128, 8, kIdescQkv, false, el);
+            mma_commit(misc + MB_W_EMPTY, el);
+            mma_commit(misc + MB_QKV_DONE, el);
             // ---- attention of head g
+            tl_event(p, tl, 110 + g, tl_n);   // QKV(g) issued
             qkv_ready.wait(misc + MB_QKV_READY);
             tc_fence_after_sync();
-            issue_scores(tmem, sb, 0);
-            mma_commit(misc + MB_S_DONE);
+            tl_event(p, tl, 120 + g, tl_n);   // QKV_READY seen
+            issue_scores(tmem, sb, 0, el);
+            mma_commit(misc + MB_S_DONE, el);
             for (int t = 0; t < 3; ++t, ++n_pv) {
               s_loaded.wait(misc + MB_S_LOADED);      // S(t) is in registers
               tc_fence_after_sync();
-              if (t < 2) { issue_scores(tmem, sb, t + 1); mma_commit(misc + MB_S_DONE); }
+              tl_event(p, tl, 130 + t, tl_n);   // S_LOADED(t) seen
+              if (t < 2) { issue_scores(tmem, sb, t + 1, el); mma_commit(misc + MB_S_DONE, el); }
               p_ready.wait(misc + MB_P_READY);         // P(t) is in TMEM
               // O accumulator n_pv & 1 was last used by P.V #(n_pv - 2): its epilogue must have read it out
               if (n_pv >= 2) mbar_wait(misc + MB_O_FREE + 8 * (n_pv & 1), ((n_pv >> 1) - 1) & 1);
               tc_fence_after_sync();
-              issue_pv(tmem, sb, n_pv & 1);
-              mma_commit(misc + MB_PV_DONE);
-              if (g == 3 && t == 2) mma_commit(misc + MB_ATTN_DONE);
+              tl_event(p, tl, 140 + t, tl_n);   // P_READY(t) seen, P.V(t) issue start
+              issue_pv(tmem, sb, n_pv & 1, el);
+              mma_commit(misc + MB_PV_DONE, el);
+              tl_event(p, tl, 150 + t, tl_n);   // P.V(t) issued
+              if (g == 3 && t == 2) mma_commit(misc + MB_ATTN_DONE, el);
             }
           }
           // ---- out_proj: needs every O epilogue of the layer (O image complete, P columns free)
@@ -497,39 +527,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             mbar_wait(misc + MB_O_FREE + 8 * (n_pv & 1), ((n_pv >> 1) - 1) & 1);
             mbar_wait(misc + MB_O_FREE + 8 * ((n_pv + 1) & 1), (((n_pv + 1) >> 1) - 1) & 1);
             tc_fence_after_sync();
+            tl_event(p, tl, 160, tl_n);   // out_proj issue start
             const uint32_t w0 = ring_wait(ring_base + 0);
             for (int t = 0; t < 3; ++t)
-              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + t * 128 * 128, 0, w0, 0, 4, kIdescN128, false);
+              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + t * 128 * 128, 0, w0, 0, 4, kIdescN128, false, el);
             ring_release(ring_base + 0);
             const uint32_t w1 = ring_wait(ring_base + 1);
             for (int t = 0; t < 3; ++t)
-              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + kXChunkBytes + t * 128 * 128, 0, w1, 0, 4, kIdescN128, true);
+              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + kXChunkBytes + t * 128 * 128, 0, w1, 0, 4, kIdescN128, true, el);
             ring_release(ring_base + 1);
-            mma_commit(misc + MB_OUT_DONE);
+            mma_commit(misc + MB_OUT_DONE, el);
+            tl_event(p, tl, 161, tl_n);   // out_proj issued
           }
           // ---- FFN: FFN1 tiles double buffered in TMEM; FFN2 partial products accumulate over the 4 hidden chunks
           x1_ready.wait(misc + MB_X1_READY);
           tc_fence_after_sync();
+          tl_event(p, tl, 170, tl_n);   // X1_READY seen
           for (int c = 0; c < 4; ++c) {
             uint32_t w1c = 0;
             for (int t = 0; t < 3; ++t, ++n_f1) {
               const int buf = n_f1 & 1;
               if (n_f1 >= 2) mbar_wait(misc + MB_F1_FREE + 8 * buf, ((n_f1 >> 1) - 1) & 1);
               tc_fence_after_sync();
+              tl_event(p, tl, 196, tl_n);   // F1_FREE seen
               if (t == 0) w1c = ring_wait(ring_base + 2 + 2 * c);          // linear1 rows 64c .. 64c+63 (K = 128)
-              issue_gemm_sw128(tmem, TM_F1 + buf * 64, sb + OFF_X + t * 128 * 128, kXChunkBytes, w1c, 64 * 128, 8, kIdescN64, false);
-              mma_commit(misc + MB_F1_DONE + 8 * buf);
+              tl_event(p, tl, 197, tl_n);   // W1 chunk resident
+              issue_gemm_sw128(tmem, TM_F1 + buf * 64, sb + OFF_X + t * 128 * 128, kXChunkBytes, w1c, 64 * 128, 8, kIdescN64, false, el);
+              mma_commit(misc + MB_F1_DONE + 8 * buf, el);
+              tl_event(p, tl, 180 + 3 * c + t, tl_n);   // FFN1(c,t) issued
               if (t == 2) ring_release(ring_base + 2 + 2 * c);
               if (t == 0 && c > 0) {
                 // FFN2 partial of the previous chunk (its hidden image is complete by now or soon)
+                tl_event(p, tl, 192, tl_n);   // waiting HID_READY
                 hid_ready.wait(misc + MB_HID_READY);
                 tc_fence_after_sync();
+                tl_event(p, tl, 193, tl_n);   // HID_READY seen
                 const uint32_t w2 = ring_wait(ring_base + 3 + 2 * (c - 1));
+                tl_event(p, tl, 194, tl_n);   // W2 chunk resident
                 for (int tt = 0; tt < 3; ++tt)
                   issue_gemm_sw128(tmem, TM_OUT + tt * 128, sb + OFF_O + ((c - 1) & 1) * kHidBytes + tt * 128 * 128, 0, w2, 0, 4,
-                                   kIdescN128, c - 1 > 0);
+                                   kIdescN128, c - 1 > 0, el);
                 ring_release(ring_base + 3 + 2 * (c - 1));
-                mma_commit(misc + MB_F2_DONE + 8 * ((c - 1) & 1));
+                mma_commit(misc + MB_F2_DONE + 8 * ((c - 1) & 1), el);
+                tl_event(p, tl, 195, tl_n);   // FFN2(c-1) issued
               }
             }
           }
@@ -538,9 +578,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           {
             const uint32_t w2 = ring_wait(ring_base + 9);
             for (int tt = 0; tt < 3; ++tt)
-              issue_gemm_sw128(tmem, TM_OUT + tt * 128, sb + OFF_O + kHidBytes + tt * 128 * 128, 0, w2, 0, 4, kIdescN128, true);
+              issue_gemm_sw128(tmem, TM_OUT + tt * 128, sb + OFF_O + kHidBytes + tt * 128 * 128, 0, w2, 0, 4, kIdescN128, true, el);
             ring_release(ring_base + 9);
-            mma_commit(misc + MB_F2_DONE + 8);
+            mma_commit(misc + MB_F2_DONE + 8, el);
+            tl_event(p, tl, 199, tl_n);   // FFN2(3) issued
           }
         }
       }
@@ -548,11 +589,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
   } else {
     // ----------------------------------------------------------------------------- compute warps
     setmaxnreg_inc<kRegsCompute>();
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int q = warp & 3, half = warp >> 2;
     const int rt = q * 32 + lane;                // row inside a 128-row tile
     const bool tile2_active = (q == 0);          // third row tile: only rows 256..287 exist
     Phase x_full, qkv_done, s_done, pv_done, out_done;
-    uint32_t n_pv = 0, n_f1 = 0;
+    uint32_t n_pv = 0, n_f1 = 0, tl_n = 0;
     const uint32_t xmax_mine = misc + MISC_XMAX + (half * 128 + rt) * 4, xmax_other = misc + MISC_XMAX + ((half ^ 1) * 128 + rt) * 4;
     const uint32_t xsum_mine = misc + MISC_XSUM + (half * 128 + rt) * 4, xsum_other = misc + MISC_XSUM + ((half ^ 1) * 128 + rt) * 4;
 
@@ -562,17 +603,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
       x_full.wait(misc + MB_X_FULL);   // the residual image is read with generic loads by the LayerNorm epilogues
 #pragma unroll 1
       for (int l = 0; l < L; ++l) {
+        const bool tl = p.timeline != nullptr && blockIdx.x == 0 && seq == (int64_t)gridDim.x && l == 1 && threadIdx.x == 0;
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           // ---- QKV epilogue of head g (warpgroup 0: row tiles 0 and 2, warpgroup 1: row tile 1)
+          tl_event(p, tl, 200 + g, tl_n);   // waiting QKV_DONE
           qkv_done.wait(misc + MB_QKV_DONE);
           tc_fence_after_sync();
+          tl_event(p, tl, 210 + g, tl_n);   // QKV_DONE seen
 #pragma unroll 1
           for (int t = 0; t < 3; ++t)
             if (t < 2 || tile2_active) epi_qkv(tmem, sb, l, g, t, q, half, lane);
           tc_fence_before_sync();
           fence_proxy_async_smem();
           warp_arrive(misc + MB_QKV_READY, lane);
+          tl_event(p, tl, 220 + g, tl_n);   // QKV epilogue done
           // ---- softmax tiles; the O epilogue of tile t-1 runs after P(t) has been handed to the tensor core
           float inv_prev = 0.f;
 #pragma unroll 1
@@ -584,24 +629,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               float m = 0.f;
               s_done.wait(misc + MB_S_DONE);
               tc_fence_after_sync();
+              tl_event(p, tl, 230 + t, tl_n);   // S_DONE(t) seen
               if (active) {
                 m = softmax_load(tmem, q, half, v);
                 st_shared_f32(xmax_mine, m);
               }
               tc_fence_before_sync();
               warp_arrive(misc + MB_S_LOADED, lane);
+              tl_event(p, tl, 240 + t, tl_n);   // S(t) loaded
               named_bar_sync(1 + q, 64);                                   // exchange the half-row maxima
               if (active) {
                 m = fmaxf(m, ld_shared_f32(xmax_other));
                 sum = softmax_exp(v, m);
               }
+              tl_event(p, tl, 250 + t, tl_n);   // exponentials done
               if (t > 0) { pv_done.wait(misc + MB_PV_DONE); tc_fence_after_sync(); }   // P.V(t-1) has consumed P
+              tl_event(p, tl, 260 + t, tl_n);   // PV_DONE(t-1) seen
               if (active) {
                 softmax_store(tmem, q, half, v);
                 st_shared_f32(xsum_mine, sum);
               }
               tc_fence_before_sync();
               warp_arrive(misc + MB_P_READY, lane);
+              tl_event(p, tl, 270 + t, tl_n);   // P(t) stored
             } else {
               pv_done.wait(misc + MB_PV_DONE);
               tc_fence_after_sync();
@@ -620,14 +670,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           }
         }
         // ---- out_proj epilogue: + bias + residual -> LayerNorm1 -> X
+        tl_event(p, tl, 280, tl_n);   // waiting OUT_DONE
         out_done.wait(misc + MB_OUT_DONE);
         tc_fence_after_sync();
+        tl_event(p, tl, 281, tl_n);   // OUT_DONE seen
 #pragma unroll 1
         for (int t = 0; t < 3; ++t)
           if (t < 2 || tile2_active) epi_ln(tmem, sb, l, 1, t, q, half, lane, xmax_mine, xmax_other, nullptr);
         tc_fence_before_sync();
         fence_proxy_async_smem();
         warp_arrive(misc + MB_X1_READY, lane);
+        tl_event(p, tl, 282, tl_n);   // LayerNorm1 done
         // ---- FFN1 epilogues: bias + GELU -> hidden chunk images
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -639,10 +692,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             float f[32];
             mbar_wait(misc + MB_F1_DONE + 8 * buf, (n_f1 >> 1) & 1);
             tc_fence_after_sync();
+            tl_event(p, tl, 300 + 3 * c + t, tl_n);   // F1_DONE(c,t) seen
             if (active) act_load(tmem, l, c, buf, q, half, f);
             tc_fence_before_sync();
             warp_arrive(misc + MB_F1_FREE + 8 * buf, lane);
             if (active) act_store(sb, c, t, p.activation, q, half, lane, f);
+            tl_event(p, tl, 320 + 3 * c + t, tl_n);   // GELU(c,t) stored
           }
           fence_proxy_async_smem();
           warp_arrive(misc + MB_HID_READY, lane);
@@ -651,6 +706,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         mbar_wait(misc + MB_F2_DONE, 1);        // FFN2(2) and FFN2(3): second completion of each barrier in this layer
         mbar_wait(misc + MB_F2_DONE + 8, 1);
         tc_fence_after_sync();
+        tl_event(p, tl, 340, tl_n);   // FFN2 complete seen
         float* ho = (l == L - 1) ? h_seq : nullptr;
 #pragma unroll 1
         for (int t = 0; t < 3; ++t)
@@ -659,13 +715,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         fence_proxy_async_smem();
         if (l == L - 1) warp_arrive(misc + MB_X_FREE, lane);
         warp_arrive(misc + MB_X2_READY, lane);
+        tl_event(p, tl, 341, tl_n);   // LayerNorm2 done
       }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
@@ -722,6 +779,10 @@ __global__ void pack_vec_kernel(LayerPackF32 L, float* __restrict__ dst, float q
   else v = L.n2_b[i - kVecN2B];
   dst[i] = v;
 }
+
+unsigned long long* g_timeline_dev = nullptr;   // diagnostics timeline buffer (device), armed by aft_selftest(102)
+unsigned long long* g_timeline_arm = nullptr;
+unsigned long long* g_timeline_host = nullptr;
 
 constexpr size_t kLayerImageBytes = 4 * kWInSlice + 32768 + 65536 + 65536;   // 262,144
 
@@ -827,6 +888,7 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   ep.num_layers = w.num_layers;
   ep.activation = activation;
   ep.nseq = nseq;
+  ep.timeline = g_timeline_arm;
   const unsigned grid = (unsigned)(nseq < sm_count ? nseq : sm_count);
   mark();
   encoder_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(ep);
@@ -891,15 +953,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_attn_kernel(const char
     mbar_init(misc + MB_P_READY, 8);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(misc + MISC_TMEM_PTR, 512); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc(misc + MISC_TMEM_PTR, 512); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(misc + MISC_TMEM_PTR));
-  if (warp < 4) {
+  if (warp >= 8) {
     setmaxnreg_dec<kRegsCtrl>();
-    if (warp == 1 && lane == 0) {
+    if (warp == kMmaWarp && lane == 0) {
       mbar_arrive_expect_tx(misc + MB_X_FULL, 3 * kQkvPart);
       bulk_g2s(sb + OFF_QKV, qkv_img, 3 * kQkvPart, misc + MB_X_FULL);
       mbar_wait(misc + MB_X_FULL, 0);
@@ -913,7 +975,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_attn_kernel(const char
     }
   } else {
     setmaxnreg_inc<kRegsCompute>();
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int q = warp & 3, half = warp >> 2;
     const int rt = q * 32 + lane;
     const bool active = tile < 2 || q == 0;
     mbar_wait(misc + MB_S_DONE, 0);
@@ -947,7 +1009,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_attn_kernel(const char
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 float bf16_round_host(float x) {
@@ -987,6 +1049,26 @@ bool tc_selftest(int which, double* max_err, cudaStream_t st) {
         cudaMemcpyToSymbol(g_wait_diag, &dev, sizeof(dev));
       }
       *max_err = 0.0;
+      return true;
+    }
+    if (which == 102) {   // arm the timeline (mapped host memory)
+      if (!g_timeline_host) {
+        g_timeline_host = static_cast<unsigned long long*>(malloc(1000 * 8));
+        if (cudaMalloc(&g_timeline_dev, 1000 * 8) != cudaSuccess) { set_error("timeline: cudaMalloc failed"); return false; }
+      }
+      g_timeline_arm = g_timeline_dev;
+      cudaMemset(g_timeline_dev, 0, 1000 * 8);
+      *max_err = 0.0;
+      return true;
+    }
+    if (which == 103) {   // dump "id clock" lines to stderr and disarm
+      unsigned long long n_ev = 0;
+      if (g_timeline_host && cudaMemcpy(g_timeline_host, g_timeline_dev, 1000 * 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+        for (int h = 0; h < 2; ++h)
+          for (unsigned long long i = 1; i <= g_timeline_host[500 * h] && i < 500; ++i, ++n_ev)
+            fprintf(stderr, "TL %llu %llu\n", g_timeline_host[500 * h + i] >> 48, g_timeline_host[500 * h + i] & 0xFFFFFFFFFFFFull);
+      g_timeline_arm = nullptr;
+      *max_err = (double)n_ev;
       return true;
     }
     int n = 0;

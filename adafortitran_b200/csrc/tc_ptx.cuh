@@ -72,6 +72,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// same, for waits that are not latency critical (producer): back off between polls so the spin does not steal
+// issue slots from the compute warps sharing the sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    ++spins;
+    if (spins == 2000000u) mbar_wait_timeout(bar, parity);
+    if (spins > 3000000u) __trap();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // proxies / fences
 // ---------------------------------------------------------------------------------------------
@@ -129,6 +141,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // K-major operand, rows of 128 bytes (64 bf16), SWIZZLE_128B: 8-row atoms of 1024 bytes
 __device__ __forceinline__ uint64_t desc_k_sw128(uint32_t saddr) { return make_smem_desc(saddr, 16, 1024, kSwizzle128); }
+// the same descriptor with a zero start address (constant part)
+__host__ __device__ constexpr uint64_t desc_k_sw128_const() {
+  return ((uint64_t)(16 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kSwizzle128 << 61);
+}
 // K-major operand, rows of 64 bytes (32 bf16), SWIZZLE_64B: 8-row atoms of 512 bytes
 __device__ __forceinline__ uint64_t desc_k_sw64(uint32_t saddr) { return make_smem_desc(saddr, 16, 512, kSwizzle64); }
 // MN-major operand, 32 contiguous MN elements (64 bytes) per K row, SWIZZLE_64B: 8 K-rows per 512-byte atom
@@ -149,26 +165,34 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 // tcgen05.mma (single thread issues), commit
 // ---------------------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] . B[smem]^T
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate,
+                                       bool elected = true) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)elected)
       : "memory");
 }
 // D[tmem] (+)= A[tmem] . B[smem]
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate,
+                                       bool elected = true) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)elected)
       : "memory");
 }
 // arrive on an mbarrier when all tcgen05.mma issued so far by this thread have completed
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void mma_commit(uint32_t bar, bool elected = true) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "setp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"((uint32_t)elected)
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

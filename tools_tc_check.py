@@ -40,6 +40,19 @@ def dump_diag():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "timeline":
+        sd = util.forti_weights(util.ada_weights())
+        m = util.make_model("forti", weights=sd, precision="bf16")
+        p, *_ = O.synthetic_batch(148 * 2, seed=3)      # 592 sequences: 4 per CTA
+        tp = torch.from_numpy(p).cuda()
+        with torch.no_grad():
+            m(tp); torch.cuda.synchronize()
+            err = C.c_double(-1)
+            _capi.lib().aft_selftest(102, C.byref(err), None)
+            m(tp); torch.cuda.synchronize()
+            _capi.lib().aft_selftest(103, C.byref(err), None)
+        print("timeline events:", err.value)
+        sys.exit(0)
     if what == "diag":
         arm_diag()
         try:

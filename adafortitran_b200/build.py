@@ -26,6 +26,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_defs():
+    """Optional compile-time switches, e.g. AFT_NVCC_DEFS="-DAFT_TC_TIMELINE -DAFT_TC_PARTS=4" (diagnostics / experiments)."""
+    return [d for d in os.environ.get("AFT_NVCC_DEFS", "").split() if d]
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -51,6 +56,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG), "include", "aft.h"))
     nvcc = _nvcc()
+    stamp = os.path.join(OBJ, "defs.stamp")
+    defs = " ".join(_extra_defs())
+    if not os.path.exists(stamp) or open(stamp).read() != defs:
+        force = True     # the compile-time switches changed: rebuild everything
+        with open(stamp, "w") as f:
+            f.write(defs)
     jobs = []
     for src in sources():
         s = os.path.join(CSRC, src)
@@ -60,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + _extra_defs() + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OBJ, os.path.basename(s) + ".log")
         with open(log, "w") as f:

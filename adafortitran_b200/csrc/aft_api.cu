@@ -412,8 +412,8 @@ int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float*
     set_error("aft_forward: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return AFT_ERR_WORKSPACE;
   }
-  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) {
-    set_error("aft_forward: workspace must be 1024-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("aft_forward: workspace must be 256-byte aligned");
     return AFT_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

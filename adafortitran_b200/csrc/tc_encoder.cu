@@ -47,7 +47,7 @@ namespace {
 using namespace ptx;
 
 #ifndef AFT_TC_PARTS
-#define AFT_TC_PARTS 2
+#define AFT_TC_PARTS 4
 #endif
 constexpr int kParts = AFT_TC_PARTS;   // threads per accumulator row = compute warpgroups (2: 8 warps x 224 regs, 4: 16 warps x 104 regs)
 static_assert(kParts == 2 || kParts == 4, "kParts must be 2 or 4");

@@ -1,0 +1,147 @@
+"""GPU: the bf16 tcgen05 path through the C-ABI.
+
+Gates (BASELINE.json north_star):
+  * official : |delta NMSE| <= 0.05 dB against the reference forward on the 21-condition synthetic sweep;
+  * self-imposed: output-relative error against the fp64 oracle <= -45 dB for FortiTran and <= -37 dB for AdaFortiTran.
+    (AdaFortiTran feeds raw SNR/delay-spread/Doppler values (up to 1400) into the token features, so at random init the
+    residual stream is dominated by metadata-driven components ~1e4 times larger than the pilot-driven ones; ANY bf16
+    operand path loses those: the reference's own bf16 autocast reaches only -33.6 dB (probe P5), a numpy
+    model of this kernel's rounding points predicts -37.7 dB, the kernel measures -39 .. -41 dB.)
+The kernel-level building blocks are checked first (aft_selftest) so a failure localises.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from adafortitran_b200 import _capi
+from oracle import aft_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return util.ada_weights()
+
+
+def run(model, pilots, snr=None, ds=None, dop=None):
+    md = util.meta(snr, ds, dop) if snr is not None else None
+    with torch.no_grad():
+        return model(torch.from_numpy(pilots), md).cpu().numpy()
+
+
+@pytest.mark.parametrize("which,tol", [(0, 1e-4), (1, 5e-3), (2, 5e-3)])
+def test_tcgen05_building_blocks(which, tol):
+    """UMMA GEMM tile (SWIZZLE_128B K-major descriptors, TMEM loads) and attention tiles (SWIZZLE_64B Q/K, MN-major V,
+    P as TMEM A operand) against a double-precision host reference inside the library."""
+    torch.zeros(1, device="cuda")
+    err = C.c_double(-1)
+    st = torch.cuda.current_stream().cuda_stream
+    _capi.check(_capi.lib().aft_selftest(which, C.byref(err), C.c_void_p(st)))
+    assert 0 <= err.value <= tol, err.value
+
+
+def test_fortitran_vs_oracle(sd):
+    g = util.golden("golden_forti.npz")
+    m = util.make_model("forti", weights=util.forti_weights(sd), precision="bf16")
+    y = run(m, g["pilots"])
+    assert O.rel_err_db(y, g["out"]) <= -45.0
+    assert O.normwise_err(y, g["out"]) <= 2e-2
+
+
+def test_adafortitran_vs_oracle(sd):
+    g = util.golden("golden_ada.npz")
+    m = util.make_model("ada", weights=sd, precision="bf16")
+    y = run(m, g["pilots"], g["snr"], g["ds"], g["dop"])
+    assert O.rel_err_db(y, g["out64"]) <= -37.0
+
+
+def test_variants_relu_layers2_sinusoidal(sd):
+    g = util.golden("golden_ada.npz")
+    v = util.golden("golden_variants.npz")
+    args = (g["pilots"][:4], g["snr"][:4], g["ds"][:4], g["dop"][:4])
+    m = util.make_model("ada", weights=sd, precision="bf16", overrides={"activation": "relu"})
+    assert O.rel_err_db(run(m, *args), v["out_relu"]) <= -36.0
+    m = util.make_model("ada", precision="bf16", overrides={"num_layers": 2},
+                        weights={k: a for k, a in sd.items() if not any(f"layers.{i}." in k for i in range(2, 6))})
+    assert O.rel_err_db(run(m, *args), v["out_layers2"]) <= -36.0
+    m = util.make_model("ada", precision="bf16", overrides={"pos_encoding_type": "sinusoidal"})
+    s2 = {k: a for k, a in sd.items() if "position_embeddings" not in k}
+    s2["transformer_encoder.positional_encoding.pe"] = m.state_dict()["transformer_encoder.positional_encoding.pe"].cpu().numpy()
+    m.load_state_dict(util.to_torch(s2))
+    assert O.rel_err_db(run(m, *args), v["out_sinusoidal"]) <= -36.0
+
+
+def test_sweep_delta_nmse(sd):
+    """21 conditions x 256 synthetic channels: NMSE of the bf16 path vs NMSE of the fp32 path (itself <= 1e-4 from the
+    reference) -- the north_star gate is 0.05 dB; also checked against the committed reference outputs."""
+    bf = util.make_model("ada", weights=sd, precision="bf16")
+    fp = util.make_model("ada", weights=sd, precision="fp32")
+    g = util.golden("golden_sweep.npz")
+    worst = 0.0
+    table = []
+    for i, (s, d, f) in enumerate(g["conds"]):
+        p, h = O.synthetic_channel(256, float(s), float(d), float(f), seed=9000 + i)
+        md = ([s] * 256, [d] * 256, [f] * 256)
+        yb, yf = run(bf, p, *md), run(fp, p, *md)
+        worst = max(worst, abs(O.nmse_db(yb, h) - O.nmse_db(yf, h)))
+        table.append(dict(snr=float(s), ds=float(d), dop=float(f), nmse_fp32_db=O.nmse_db(yf, h), nmse_bf16_db=O.nmse_db(yb, h),
+                          mse_ref_def_fp32_db=O.mse_db_reference(yf, h), bf16_vs_fp32_rel_err_db=O.rel_err_db(yb, yf)))
+        # conditioning degrades with the raw metadata magnitude (Doppler up to 1400): informational floor only
+        assert O.rel_err_db(yb, yf) <= -30.0, (i, table[-1])
+        # the committed reference outputs for this condition (4 samples)
+        yr = run(bf, g["pilots"][i], *( [s] * 4, [d] * 4, [f] * 4))
+        assert abs(O.nmse_db(yr, g["truth"][i]) - O.nmse_db(g["out"][i], g["truth"][i])) <= 0.05, i
+    import json, os
+    os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(util.ROOT, "gpurun_out", "sweep_bf16_vs_fp32.json"), "w") as fh:
+        json.dump(dict(worst_delta_nmse_db=worst, conditions=table), fh, indent=1)
+    assert worst <= 0.05, worst
+
+
+def test_ragged_and_chunked_batches(sd):
+    """Batch sizes that do not fill the persistent grid (1, 3, 75 = 150 sequences > 148 CTAs) and one that crosses the
+    internal chunk boundary (8192 + 3); properties: determinism, permutation equivariance, re/im independence."""
+    m = util.make_model("forti", weights=util.forti_weights(sd), precision="bf16")
+    cfg = util.oracle_cfg("forti")
+    for b, seed in ((1, 31), (3, 32), (75, 33)):
+        p, *_ = O.synthetic_batch(b, seed=seed)
+        ref = O.forward(cfg, util.forti_weights(sd), p)
+        assert O.rel_err_db(run(m, p), ref) <= -45.0, b
+    b = 8192 + 3
+    p, *_ = O.synthetic_batch(b, seed=34)
+    y = run(m, p)
+    assert np.isfinite(y.view(np.float32)).all()
+    assert np.array_equal(run(m, p), y)                     # deterministic
+    perm = np.random.default_rng(1).permutation(b)
+    assert np.array_equal(run(m, p[perm]), y[perm])         # sequences are independent
+    p2 = (p.real + 1j * np.roll(p.imag, 1, axis=0)).astype(np.complex64)
+    assert np.array_equal(run(m, p2).real, y.real)
+    idx = [0, 8191, 8192, b - 1]
+    assert O.rel_err_db(y[idx], O.forward(cfg, util.forti_weights(sd), p[idx])) <= -45.0
+
+
+def test_host_entry_point_bf16(sd):
+    m = util.make_model("ada", weights=sd, precision="bf16")
+    p, snr, ds, dop = O.synthetic_batch(2048 + 9, seed=35)
+    y = run(m, p, snr, ds, dop)
+    yh = m.forward_host(torch.from_numpy(p), util.meta(snr, ds, dop)).numpy()
+    assert np.array_equal(y, yh)
+
+
+def test_empty_batch_and_profile_api(sd):
+    m = util.make_model("forti", weights=util.forti_weights(sd), precision="bf16")
+    with torch.no_grad():
+        assert m(torch.zeros(0, 12, 2, dtype=torch.cfloat)).shape == (0, 120, 14)
+        m(torch.zeros(4, 12, 2, dtype=torch.cfloat))
+        lib = _capi.lib()
+        _capi.check(lib.aft_profile_enable(m._handle, 1))
+        n0 = lib.aft_launch_count()
+        m(torch.zeros(4, 12, 2, dtype=torch.cfloat))
+        ms, nl = (C.c_double * 3)(), (C.c_int64 * 3)()
+        _capi.check(lib.aft_profile_read(m._handle, ms, nl))
+        assert lib.aft_launch_count() - n0 == 3 and list(nl) == [1, 1, 1] and all(t > 0 for t in ms)
+        _capi.check(lib.aft_profile_enable(m._handle, 0))

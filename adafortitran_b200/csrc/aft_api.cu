@@ -379,7 +379,7 @@ int aft_load_weights(AftHandle* h, const AftWeights* w, void* stream) {
     for (const auto& it : items)
       if (!copy_to(it.s, it.d, it.n, st, it.name)) return AFT_ERR_CUDA;
   }
-  if (!tc_weights_pack(h->tc, h->layers, st)) return AFT_ERR_CUDA;
+  if (!tc_weights_pack(h->tc, h->layers, h->front.enh, h->head.refine, st)) return AFT_ERR_CUDA;
   if (!check_launch("aft_load_weights")) return AFT_ERR_CUDA;
   h->loaded = true;
   return AFT_OK;

@@ -100,6 +100,14 @@ bool launch_frontend(const FrontPack& p, const float2* pilots, const float* snr,
 // head.cu : linear_2 -> fold -> + enh -> ConvEnhancer -> interleaved complex store
 bool launch_head(const HeadPack& p, const float* h, const float* enh, float2* out, int64_t nsamples, cudaStream_t st);
 
+// conv_tc.cu : the same two stages for the AFT_BF16 path, ConvEnhancer on the tensor cores (persistent CTAs)
+size_t conv_tc_pack_bytes();
+bool conv_tc_pack(const ConvPack& src, void* dst, cudaStream_t st);
+bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilots, const float* snr, const float* ds,
+                        const float* dop, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st);
+bool launch_head_tc(const HeadPack& p, const void* pack, const float* h, const float* enh, float2* out, int64_t nsamples,
+                    int sm_count, cudaStream_t st);
+
 // gemm_f32.cu : C[M,N] = A[M,K] * W[N,K]^T + bias, fp32 FMA
 enum GemmEpi { kEpiBias = 0, kEpiBiasAct = 1, kEpiBiasResLn = 2 };
 bool launch_gemm_f32(int epi, const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,

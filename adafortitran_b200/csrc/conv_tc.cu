@@ -1,0 +1,243 @@
+// Frontend and head of the AFT_BF16 path with the ConvEnhancer stacks on the tensor cores (conv_tc.cuh).
+//   frontend_tc : pilots -> Linear(24,1680) -> ConvEnhancer -> Unfold(3x2) [+ ChannelAdapter] -> linear_1 + pos -> X image
+//   head_tc     : linear_2 -> Fold -> + conv_enhanced -> ConvEnhancer -> complex64
+// Same math and reference citations as frontend.cu / head.cu; persistent CTAs (the zero-padded activation planes,
+// the packed weights and the TMEM allocation are set up once per CTA).
+#include "conv_tc.cuh"
+
+namespace aft {
+
+using namespace convtc;
+
+namespace {
+
+__global__ void __launch_bounds__(kThreads, 1)
+frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* __restrict__ pilots, const float* __restrict__ snr,
+                   const float* __restrict__ ds, const float* __restrict__ dop, float* __restrict__ enh_out,
+                   __nv_bfloat16* __restrict__ hb_out, int64_t nseq) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  if ((sb & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar = sb + OFF_BAR;
+  float* xin = reinterpret_cast<float*>(smem + OFF_BAR + 64);   // [24]
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); fence_mbar_init(); }
+  if (warp == 1) { tmem_alloc(bar + 16, 512); tmem_relinquish(); }
+  stack_init(smem, pack);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(bar + 16));
+
+  float* in = reinterpret_cast<float*>(smem + OFF_IN);
+  const float* enh = reinterpret_cast<const float*>(smem + OFF_OUT);
+  float* tok = reinterpret_cast<float*>(smem + OFF_SCRATCH);   // [280][in_dim]
+  float* z = tok + 3360;                                       // [3][560]
+  float* w1t = z + 1680;                                       // [in_dim][128]
+  float* hid = w1t + 1536;                                     // [2][64]
+  const int in_dim = p.in_dim;
+  uint32_t n_run = 0;
+
+  for (int64_t seq = blockIdx.x; seq < nseq; seq += gridDim.x, ++n_run) {
+    const int64_t sample = seq >> 1;
+    if (tid < kPilots) {
+      const float2 v = pilots[sample * kPilots + tid];
+      xin[tid] = (seq & 1) ? v.y : v.x;
+    }
+    __syncthreads();
+    // upsample (fortitran.py:203) into the padded fp32 plane
+    for (int pix = tid; pix < kPix; pix += kThreads) {
+      float acc = p.up_b[pix];
+#pragma unroll
+      for (int k = 0; k < kPilots; ++k) acc = fmaf(p.up_wt[k * kPix + pix], xin[k], acc);
+      const int r = pix / kGridW, c = pix - r * kGridW;
+      in[(r + 1) * kPW + c + 1] = acc;
+    }
+    __syncthreads();
+    stack_run(smem, sb, tmem, bar, n_run);                      // fortitran.py:209
+    for (int i = tid; i < kPix; i += kThreads) enh_out[seq * kPix + i] = enh[i];
+
+    // tokens = [patch(6) | adaptive(6)]  (fortitran.py:212-217)
+    for (int i = tid; i < kS * kPatchLen; i += kThreads) {
+      const int t = i / kPatchLen, f = i - t * kPatchLen;
+      const int pi = t / kTokW, pj = t - pi * kTokW;
+      const int a = f / kPatchW, b = f - a * kPatchW;
+      tok[t * in_dim + f] = enh[(kPatchH * pi + a) * kGridW + kPatchW * pj + b];
+    }
+    for (int i = tid; i < in_dim * kD; i += kThreads) w1t[i] = p.l1_wt[i];
+    if (p.adaptive) {
+      const float cond[3] = {snr[sample], ds[sample], dop[sample]};
+      for (int m = 0; m < 3; ++m) {
+        const MlpPack& mp = p.mlp[m];
+        if (tid < p.h1) hid[tid] = fmaxf(fmaf(mp.w0[tid], cond[m], mp.b0[tid]), 0.f);
+        __syncthreads();
+        if (tid < p.h2) {
+          float acc = mp.b1[tid];
+          for (int k = 0; k < p.h1; ++k) acc = fmaf(mp.w1[tid * p.h1 + k], hid[k], acc);
+          hid[64 + tid] = fmaxf(acc, 0.f);
+        }
+        __syncthreads();
+        for (int j = tid; j < 2 * kS; j += kThreads) {
+          float acc = mp.b2[j];
+          for (int k = 0; k < p.h2; ++k) acc = fmaf(mp.w2t[k * 2 * kS + j], hid[64 + k], acc);
+          z[m * 2 * kS + j] = acc;
+        }
+        __syncthreads();
+      }
+      for (int i = tid; i < kS * kAda; i += kThreads) {
+        const int t = i / kAda, f = i - t * kAda;
+        tok[t * in_dim + kPatchLen + f] = z[(f >> 1) * 2 * kS + 2 * t + (f & 1)];
+      }
+    }
+    __syncthreads();
+    // h = tok . W1^T + b1 + pos (encoders.py:67-68) -> bf16 operand image of the residual stream
+    char* base = reinterpret_cast<char*>(hb_out) + seq * (int64_t)kXImageBytes;
+    for (int it = tid; it < kSPad * (kD / 8); it += kThreads) {
+      const int t = it >> 4, c8 = (it & 15) * 8;
+      uint4 pk = make_uint4(0, 0, 0, 0);   // rows 280..287 are zero padding
+      if (t < kS) {
+        const float4 pa = *reinterpret_cast<const float4*>(p.posb + t * kD + c8);
+        const float4 pb = *reinterpret_cast<const float4*>(p.posb + t * kD + c8 + 4);
+        float acc[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+        for (int k = 0; k < in_dim; ++k) {
+          const float a = tok[t * in_dim + k];
+          const float4 wa = *reinterpret_cast<const float4*>(w1t + k * kD + c8);
+          const float4 wb = *reinterpret_cast<const float4*>(w1t + k * kD + c8 + 4);
+          acc[0] = fmaf(a, wa.x, acc[0]); acc[1] = fmaf(a, wa.y, acc[1]);
+          acc[2] = fmaf(a, wa.z, acc[2]); acc[3] = fmaf(a, wa.w, acc[3]);
+          acc[4] = fmaf(a, wb.x, acc[4]); acc[5] = fmaf(a, wb.y, acc[5]);
+          acc[6] = fmaf(a, wb.z, acc[6]); acc[7] = fmaf(a, wb.w, acc[7]);
+        }
+        pk = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      }
+      *reinterpret_cast<uint4*>(base + ximage_offset(t, c8)) = pk;
+    }
+    __syncthreads();   // scratch / result are overwritten by the next image
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const float* __restrict__ h, const float* __restrict__ enh,
+               float* __restrict__ out /* interleaved re/im */, int64_t nsamples) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  if ((sb & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = sb + OFF_BAR;
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); fence_mbar_init(); }
+  if (warp == 1) { tmem_alloc(bar + 16, 512); tmem_relinquish(); }
+  stack_init(smem, pack);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(bar + 16));
+
+  float* in = reinterpret_cast<float*>(smem + OFF_IN);
+  const float* res = reinterpret_cast<const float*>(smem + OFF_OUT);
+  float4 w2[kPatchLen];
+#pragma unroll
+  for (int f = 0; f < kPatchLen; ++f) w2[f] = *reinterpret_cast<const float4*>(p.l2_w + f * kD + lane * 4);
+  const float b2 = lane < kPatchLen ? p.l2_b[lane] : 0.f;
+  uint32_t n_run = 0;
+
+  for (int64_t sample = blockIdx.x; sample < nsamples; sample += gridDim.x) {
+    for (int part = 0; part < 2; ++part, ++n_run) {
+      const int64_t seq = 2 * sample + part;
+      const float* hs = h + seq * (int64_t)kS * kD;
+      const float* es = enh + seq * (int64_t)kPix;
+      // linear_2 (encoders.py:70), Fold (patch_processors.py:69-71) and the residual (fortitran.py:228)
+      for (int t = warp; t < kS; t += kThreads / 32) {
+        const float4 hv = *reinterpret_cast<const float4*>(hs + t * kD + lane * 4);
+        float acc[kPatchLen];
+#pragma unroll
+        for (int f = 0; f < kPatchLen; ++f) acc[f] = hv.x * w2[f].x + hv.y * w2[f].y + hv.z * w2[f].z + hv.w * w2[f].w;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+          for (int f = 0; f < kPatchLen; ++f) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], off);
+        if (lane < kPatchLen) {
+          float v = acc[0];
+#pragma unroll
+          for (int f = 1; f < kPatchLen; ++f) v = (lane == f) ? acc[f] : v;
+          const int pi = t / kTokW, pj = t - pi * kTokW;
+          const int a = lane / kPatchW, b = lane - a * kPatchW;
+          const int r = kPatchH * pi + a, c = kPatchW * pj + b;
+          in[(r + 1) * kPW + c + 1] = v + b2 + es[r * kGridW + c];
+        }
+      }
+      __syncthreads();
+      stack_run(smem, sb, tmem, bar, n_run);                    // fortitran.py:231
+      // torch.complex (fortitran.py:180): this pass owns the real or the imaginary half of every element
+      for (int i = tid; i < kPix; i += kThreads) out[(sample * kPix + i) * 2 + part] = res[i];
+      __syncthreads();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// fp32 ConvEnhancer parameters (SIMT packing, ConvPack) -> tensor-core pack (conv_tc.cuh layout)
+__global__ void conv_tc_pack_kernel(ConvPack src, uint8_t* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(dst + kPkW2);
+  __nv_bfloat16* w3 = reinterpret_cast<__nv_bfloat16*>(dst + kPkW3);
+  float* f = reinterpret_cast<float*>(dst + kPkF32);
+  if (i < 9 * 512) {           // conv2: [tap][half][cout 32][8]; half 1 (input channels 8..15) is zero
+    const int t = i / 512, rem = i % 512, half = rem / 256, co = (rem % 256) / 8, j = rem % 8;
+    w2[i] = __float2bfloat16(half == 0 ? src.w1[(t * 8 + j) * 32 + co] : 0.f);   // src.w1 is [tap][cin 8][cout 32]
+  }
+  if (i < 18 * 256) {          // conv3: [tap][kstep][half][cout 16][8]; couts 8..15 are zero
+    const int tk = i / 256, rem = i % 256, half = rem / 128, co = (rem % 128) / 8, j = rem % 8;
+    const int t = tk >> 1, ks = tk & 1, ci = ks * 16 + half * 8 + j;
+    w3[i] = __float2bfloat16(co < 8 ? src.w2[(t * 32 + ci) * 8 + co] : 0.f);     // src.w2 is [tap][cin 32][cout 8]
+  }
+  if (i < 72) { f[kF_w0 + i] = src.w0[i]; f[kF_w3 + i] = src.w3[i]; }
+  if (i < 8) { f[kF_b0 + i] = src.b0[i]; f[kF_b2 + i] = src.b2[i]; }
+  if (i < 32) f[kF_b1 + i] = src.b1[i];
+  if (i == 0) f[kF_b3] = src.b3[0];
+}
+
+}  // namespace
+
+size_t conv_tc_pack_bytes() { return kPkBytes; }
+
+bool conv_tc_pack(const ConvPack& src, void* dst, cudaStream_t st) {
+  conv_tc_pack_kernel<<<(9 * 512 + 255) / 256, 256, 0, st>>>(src, static_cast<uint8_t*>(dst));
+  count_launch();
+  return check_launch("conv_tc_pack_kernel");
+}
+
+bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilots, const float* snr, const float* ds,
+                        const float* dop, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st) {
+  if (cudaFuncSetAttribute(frontend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStackSmemBytes) != cudaSuccess) {
+    set_error("frontend_tc: cannot opt in to %d bytes of shared memory: %s", kStackSmemBytes, cudaGetErrorString(cudaGetLastError()));
+    return false;
+  }
+  if (nsamples <= 0) return true;
+  const int64_t nseq = 2 * nsamples;
+  frontend_tc_kernel<<<(unsigned)(nseq < sm_count ? nseq : sm_count), kThreads, kStackSmemBytes, st>>>(
+      p, static_cast<const uint8_t*>(pack), pilots, snr, ds, dop, enh, hb, nseq);
+  count_launch();
+  return check_launch("frontend_tc_kernel");
+}
+
+bool launch_head_tc(const HeadPack& p, const void* pack, const float* h, const float* enh, float2* out, int64_t nsamples,
+                    int sm_count, cudaStream_t st) {
+  if (cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStackSmemBytes) != cudaSuccess) {
+    set_error("head_tc: cannot opt in to %d bytes of shared memory: %s", kStackSmemBytes, cudaGetErrorString(cudaGetLastError()));
+    return false;
+  }
+  if (nsamples <= 0) return true;
+  head_tc_kernel<<<(unsigned)(nsamples < sm_count ? nsamples : sm_count), kThreads, kStackSmemBytes, st>>>(
+      p, static_cast<const uint8_t*>(pack), h, enh, reinterpret_cast<float*>(out), nsamples);
+  count_launch();
+  return check_launch("head_tc_kernel");
+}
+
+}  // namespace aft

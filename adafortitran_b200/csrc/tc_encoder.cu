@@ -878,7 +878,8 @@ bool tc_weights_alloc(TcWeights& w, int num_layers) {
   w.layers.assign(num_layers, TcLayer{});
   // arena: per layer the operand images + the epilogue vectors; then the device copy of the table
   const size_t per_layer = kLayerImageBytes + kVecPerLayer * sizeof(float);
-  w.arena_bytes = num_layers * per_layer + num_layers * sizeof(TcLayer) + 1024;
+  const size_t conv_bytes = (conv_tc_pack_bytes() + 255) / 256 * 256;
+  w.arena_bytes = num_layers * per_layer + (num_layers * sizeof(TcLayer) + 255) / 256 * 256 + 2 * conv_bytes + 1024;
   if (cudaMalloc(&w.arena, w.arena_bytes) != cudaSuccess) {
     set_error("tc_weights_alloc: cudaMalloc(%zu) failed: %s", w.arena_bytes, cudaGetErrorString(cudaGetLastError()));
     w.arena = nullptr;
@@ -899,6 +900,8 @@ bool tc_weights_alloc(TcWeights& w, int num_layers) {
     T.n1_w = blk + kVecN1W; T.n1_b = blk + kVecN1B; T.n2_w = blk + kVecN2W; T.n2_b = blk + kVecN2B;
   }
   w.layers_dev = reinterpret_cast<TcLayer*>(base + num_layers * per_layer);
+  w.conv_front = base + num_layers * per_layer + (num_layers * sizeof(TcLayer) + 255) / 256 * 256;
+  w.conv_head = static_cast<char*>(w.conv_front) + conv_bytes;
   return true;
 }
 
@@ -907,7 +910,8 @@ void tc_weights_free(TcWeights& w) {
   w.arena = nullptr;
 }
 
-bool tc_weights_pack(TcWeights& w, const std::vector<LayerPackF32>& src, cudaStream_t st) {
+bool tc_weights_pack(TcWeights& w, const std::vector<LayerPackF32>& src, const ConvPack& enh, const ConvPack& refine, cudaStream_t st) {
+  if (!conv_tc_pack(enh, w.conv_front, st) || !conv_tc_pack(refine, w.conv_head, st)) return false;
   const float qscale = 1.4426950408889634f / sqrtf((float)kDh);   // log2(e) / sqrt(dh): softmax runs on exp2
   for (int l = 0; l < w.num_layers; ++l) {
     const LayerPackF32& S = src[l];
@@ -950,7 +954,7 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   char* ximg = ws + align_up_sz(nseq * kPix * sizeof(float), 1024);
   float* hout = reinterpret_cast<float*>(ximg + align_up_sz(nseq * (size_t)kXImageBytes, 1024));
   mark();
-  if (!launch_frontend(front, pilots, snr, ds, dop, enh, nullptr, reinterpret_cast<__nv_bfloat16*>(ximg), nsamples, st)) return false;
+  if (!launch_frontend_tc(front, w.conv_front, pilots, snr, ds, dop, enh, reinterpret_cast<__nv_bfloat16*>(ximg), nsamples, sm_count, st)) return false;
   if (cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes) != cudaSuccess) {
     set_error("encoder_kernel: cannot opt in to %u bytes of shared memory: %s", kTcSmemBytes, cudaGetErrorString(cudaGetLastError()));
     return false;
@@ -969,7 +973,7 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   count_launch();
   if (!check_launch("encoder_kernel")) return false;
   mark();
-  const bool ok = launch_head(head, hout, enh, out, nsamples, st);
+  const bool ok = launch_head_tc(head, w.conv_head, hout, enh, out, nsamples, sm_count, st);
   mark();
   return ok;
 }

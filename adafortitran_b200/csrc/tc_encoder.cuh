@@ -23,11 +23,13 @@ struct TcWeights {
   int num_layers = 0;
   TcLayer* layers_dev = nullptr;        // device copy of the table
   std::vector<TcLayer> layers;          // host copy
+  void* conv_front = nullptr;           // tensor-core packs of the two ConvEnhancers (conv_tc.cuh), inside the arena
+  void* conv_head = nullptr;
 };
 
 bool tc_weights_alloc(TcWeights& w, int num_layers);
 void tc_weights_free(TcWeights& w);
-bool tc_weights_pack(TcWeights& w, const std::vector<LayerPackF32>& src, cudaStream_t st);
+bool tc_weights_pack(TcWeights& w, const std::vector<LayerPackF32>& src, const ConvPack& enh, const ConvPack& refine, cudaStream_t st);
 size_t tc_workspace_bytes(int64_t chunk_samples);
 struct TcProfileHook {
   void (*mark)(void* ctx, cudaStream_t st);   // nullptr when profiling is off

@@ -1,7 +1,7 @@
 """GPU scratch check of the tcgen05 path: self-tests, then bf16 forward vs oracle."""
 import ctypes as C, json, os, sys, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adafortitran_b200 import _capi
 from oracle import aft_oracle as O
 from tests import util

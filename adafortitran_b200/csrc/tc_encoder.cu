@@ -551,8 +551,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           // X and the accumulator columns [0,384) are free once the previous LayerNorm2 has finished
           if (n_layers_done > 0) x2_ready.wait(misc + MB_X2_READY);
           tc_fence_after_sync();
-          for (int g = 0; g < 4; ++g, ++n_in) {
-            // ---- QKV projection of head g, three row tiles (queues behind P.V(g-1, 2))
+          auto issue_qkv = [&](int g) {   // QKV projection of head g, three row tiles; accumulators alias the S columns
             mbar_wait(misc + MB_W_FULL, n_in & 1);
             tc_fence_after_sync();
             tl_event(p, tl, 100 + g, tl_n);   // QKV(g) issue start
@@ -560,8 +559,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               issue_gemm_sw128(tmem, TM_QKV + t * 96, sb + OFF_X + t * 128 * 128, kXChunkBytes, sb + OFF_W, 96 * 128, 8, kIdescQkv, false, el);
             mma_commit(misc + MB_W_EMPTY, el);
             mma_commit(misc + MB_QKV_DONE, el);
-            // ---- attention of head g
             tl_event(p, tl, 110 + g, tl_n);   // QKV(g) issued
+            ++n_in;
+          };
+          issue_qkv(0);
+          for (int g = 0; g < 4; ++g) {
+            // ---- attention of head g
             qkv_ready.wait(misc + MB_QKV_READY);
             tc_fence_after_sync();
             tl_event(p, tl, 120 + g, tl_n);   // QKV_READY seen
@@ -572,6 +575,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               tc_fence_after_sync();
               tl_event(p, tl, 130 + t, tl_n);   // S_LOADED(t) seen
               if (t < 2) { issue_scores(tmem, sb, t + 1, el); mma_commit(misc + MB_S_DONE, el); }
+              // the S columns are free after the last tile: the next head's projection runs under this tile's exponentials
+              // (it only reads X and the weight slot; the Q/K/V images are rewritten later, by the epilogue)
+              else if (g < 3) issue_qkv(g + 1);
               p_ready.wait(misc + MB_P_READY);         // P(t) is in TMEM
               // O accumulator n_pv & 1 was last used by P.V #(n_pv - 2): its epilogue must have read it out
               if (n_pv >= 2) mbar_wait(misc + MB_O_FREE + 8 * (n_pv & 1), ((n_pv >> 1) - 1) & 1);

@@ -102,6 +102,7 @@ bool launch_head(const HeadPack& p, const float* h, const float* enh, float2* ou
 
 // conv_tc.cu : the same two stages for the AFT_BF16 path, ConvEnhancer on the tensor cores (persistent CTAs)
 size_t conv_tc_pack_bytes();
+void conv_tc_dump_timeline();
 bool conv_tc_pack(const ConvPack& src, void* dst, cudaStream_t st);
 bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilots, const float* snr, const float* ds,
                         const float* dop, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st);

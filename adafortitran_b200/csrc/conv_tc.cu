@@ -3,6 +3,8 @@
 //   head_tc     : linear_2 -> Fold -> + conv_enhanced -> ConvEnhancer -> complex64
 // Same math and reference citations as frontend.cu / head.cu; persistent CTAs (the zero-padded activation planes,
 // the packed weights and the TMEM allocation are set up once per CTA).
+#include <cstdio>
+
 #include "conv_tc.cuh"
 
 namespace aft {
@@ -10,6 +12,45 @@ namespace aft {
 using namespace convtc;
 
 namespace {
+
+// One item = (token row t, 8 consecutive model columns): 288 x 16 items = 9 per thread, processed three at a time so
+// that the six 16-byte reads of the positional table (L2 resident, 143 KB) of a batch are in flight together.
+template <int IN_DIM>
+__device__ __forceinline__ void linear1_image(const float* __restrict__ posb, const float* tok, const float* w1t, char* base) {
+  constexpr int kItems = kSPad * (kD / 8), kPerThread = kItems / kThreads;   // 4608 / 512 = 9
+  static_assert(kItems % kThreads == 0 && kPerThread % 3 == 0, "item count must split evenly");
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int b0 = 0; b0 < kPerThread; b0 += 3) {
+    float4 pa[3], pb[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int it = tid + (b0 + j) * kThreads, t = it >> 4, c8 = (it & 15) * 8;
+      const int tt = t < kS ? t : 0;   // rows 280..287 are zero padding (computed on a valid row, stored as zeros)
+      pa[j] = *reinterpret_cast<const float4*>(posb + tt * kD + c8);
+      pb[j] = *reinterpret_cast<const float4*>(posb + tt * kD + c8 + 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int it = tid + (b0 + j) * kThreads, t = it >> 4, c8 = (it & 15) * 8;
+      const int tt = t < kS ? t : 0;
+      float acc[8] = {pa[j].x, pa[j].y, pa[j].z, pa[j].w, pb[j].x, pb[j].y, pb[j].z, pb[j].w};
+#pragma unroll
+      for (int k = 0; k < IN_DIM; ++k) {
+        const float a = tok[tt * IN_DIM + k];
+        const float4 wa = *reinterpret_cast<const float4*>(w1t + k * kD + c8);
+        const float4 wb = *reinterpret_cast<const float4*>(w1t + k * kD + c8 + 4);
+        acc[0] = fmaf(a, wa.x, acc[0]); acc[1] = fmaf(a, wa.y, acc[1]);
+        acc[2] = fmaf(a, wa.z, acc[2]); acc[3] = fmaf(a, wa.w, acc[3]);
+        acc[4] = fmaf(a, wb.x, acc[4]); acc[5] = fmaf(a, wb.y, acc[5]);
+        acc[6] = fmaf(a, wb.z, acc[6]); acc[7] = fmaf(a, wb.w, acc[7]);
+      }
+      uint4 pk = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      if (t >= kS) pk = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(base + ximage_offset(t, c8)) = pk;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* __restrict__ pilots, const float* __restrict__ snr,
@@ -46,6 +87,10 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
       xin[tid] = (seq & 1) ? v.y : v.x;
     }
     __syncthreads();
+#ifdef AFT_TC_TIMELINE
+    const bool st_on = blockIdx.x == 0 && n_run == 2 && tid == 0;
+    if (st_on) g_conv_tl[10] = clock64();
+#endif
     // upsample (fortitran.py:203) into the padded fp32 plane
     for (int pix = tid; pix < kPix; pix += kThreads) {
       float acc = p.up_b[pix];
@@ -55,7 +100,13 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
       in[(r + 1) * kPW + c + 1] = acc;
     }
     __syncthreads();
+#ifdef AFT_TC_TIMELINE
+    if (st_on) g_conv_tl[11] = clock64();
+#endif
     stack_run(smem, sb, tmem, bar, n_run);                      // fortitran.py:209
+#ifdef AFT_TC_TIMELINE
+    if (st_on) g_conv_tl[12] = clock64();
+#endif
     for (int i = tid; i < kPix; i += kThreads) enh_out[seq * kPix + i] = enh[i];
 
     // tokens = [patch(6) | adaptive(6)]  (fortitran.py:212-217)
@@ -91,29 +142,16 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
       }
     }
     __syncthreads();
+#ifdef AFT_TC_TIMELINE
+    if (st_on) g_conv_tl[13] = clock64();
+#endif
     // h = tok . W1^T + b1 + pos (encoders.py:67-68) -> bf16 operand image of the residual stream
-    char* base = reinterpret_cast<char*>(hb_out) + seq * (int64_t)kXImageBytes;
-    for (int it = tid; it < kSPad * (kD / 8); it += kThreads) {
-      const int t = it >> 4, c8 = (it & 15) * 8;
-      uint4 pk = make_uint4(0, 0, 0, 0);   // rows 280..287 are zero padding
-      if (t < kS) {
-        const float4 pa = *reinterpret_cast<const float4*>(p.posb + t * kD + c8);
-        const float4 pb = *reinterpret_cast<const float4*>(p.posb + t * kD + c8 + 4);
-        float acc[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-        for (int k = 0; k < in_dim; ++k) {
-          const float a = tok[t * in_dim + k];
-          const float4 wa = *reinterpret_cast<const float4*>(w1t + k * kD + c8);
-          const float4 wb = *reinterpret_cast<const float4*>(w1t + k * kD + c8 + 4);
-          acc[0] = fmaf(a, wa.x, acc[0]); acc[1] = fmaf(a, wa.y, acc[1]);
-          acc[2] = fmaf(a, wa.z, acc[2]); acc[3] = fmaf(a, wa.w, acc[3]);
-          acc[4] = fmaf(a, wb.x, acc[4]); acc[5] = fmaf(a, wb.y, acc[5]);
-          acc[6] = fmaf(a, wb.z, acc[6]); acc[7] = fmaf(a, wb.w, acc[7]);
-        }
-        pk = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
-      }
-      *reinterpret_cast<uint4*>(base + ximage_offset(t, c8)) = pk;
-    }
+    if (in_dim == kPatchLen) linear1_image<kPatchLen>(p.posb, tok, w1t, reinterpret_cast<char*>(hb_out) + seq * (int64_t)kXImageBytes);
+    else linear1_image<kPatchLen + kAda>(p.posb, tok, w1t, reinterpret_cast<char*>(hb_out) + seq * (int64_t)kXImageBytes);
     __syncthreads();   // scratch / result are overwritten by the next image
+#ifdef AFT_TC_TIMELINE
+    if (st_on) g_conv_tl[14] = clock64();
+#endif
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -206,6 +244,17 @@ __global__ void conv_tc_pack_kernel(ConvPack src, uint8_t* __restrict__ dst) {
 }  // namespace
 
 size_t conv_tc_pack_bytes() { return kPkBytes; }
+
+// diagnostics (-DAFT_TC_TIMELINE builds): prints the phase durations of the stamped stack run
+void conv_tc_dump_timeline() {
+#ifdef AFT_TC_TIMELINE
+  unsigned long long t[32];
+  if (cudaMemcpyFromSymbol(t, g_conv_tl, sizeof(t)) != cudaSuccess) return;
+  const char* names[] = {"conv1", "conv2 issue", "conv2 wait", "conv2 epilogue", "conv3 issue", "conv3 wait", "conv3 epilogue", "conv4"};
+  for (int i = 0; i < 8; ++i) fprintf(stderr, "CONV %-15s %llu\n", names[i], t[i + 1] - t[i]);
+  fprintf(stderr, "CONV frontend: upsample %llu | stack %llu | enh store+tokens %llu | linear_1 %llu\n", t[11] - t[10], t[12] - t[11], t[13] - t[12], t[14] - t[13]);
+#endif
+}
 
 bool conv_tc_pack(const ConvPack& src, void* dst, cudaStream_t st) {
   conv_tc_pack_kernel<<<(9 * 512 + 255) / 256, 256, 0, st>>>(src, static_cast<uint8_t*>(dst));

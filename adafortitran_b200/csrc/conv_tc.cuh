@@ -53,6 +53,19 @@ constexpr int OFF_SCRATCH = OFF_MID + kPlaneBytes + kPosGuard * 16; // 32,768 by
 __device__ __forceinline__ uint64_t desc_k_none(uint32_t saddr, uint32_t lbo_bytes) {
   return make_smem_desc(saddr, lbo_bytes, 128, kSwizzleNone);   // SBO = 128: next 8 rows (positions / couts)
 }
+// the same split in a constant high word (SBO, version, layout) and a low word (LBO << 16 | address >> 4) so that the
+// issue loops only add to the low word
+constexpr uint32_t kDescHiNone = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo_none(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo) { return ((uint64_t)kDescHiNone << 32) | lo; }
+
+// diagnostics: phase stamps of one stack run (block 0, thread 0), only in -DAFT_TC_TIMELINE builds
+#ifdef AFT_TC_TIMELINE
+__device__ unsigned long long g_conv_tl[32];
+#define AFT_CONV_STAMP(i) do { if (stamp_on && threadIdx.x == 0) g_conv_tl[i] = clock64(); } while (0)
+#else
+#define AFT_CONV_STAMP(i) do { } while (0)
+#endif
 
 constexpr uint32_t kIdescConv2 = make_idesc_bf16(128, 32, false, false);
 constexpr uint32_t kIdescConv3 = make_idesc_bf16(128, 16, false, false);
@@ -78,6 +91,8 @@ __device__ __forceinline__ void stack_init(uint8_t* smem, const uint8_t* __restr
 // (count 1 each), `phase` = number of stacks this CTA has run before (parity of both barriers).
 __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t tmem, uint32_t bar, uint32_t phase) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool stamp_on = blockIdx.x == 0 && phase == 2; (void)stamp_on;
+  AFT_CONV_STAMP(0);
   const float* fw = reinterpret_cast<const float*>(smem + OFF_PK + kPkF32);
   const float* in = reinterpret_cast<const float*>(smem + OFF_IN);
 
@@ -90,8 +105,9 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float a = in[(r + t / 3) * kPW + c + t % 3];
-#pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = fmaf(a, fw[kF_w0 + t * 8 + o], acc[o]);
+      const float4 wa = *reinterpret_cast<const float4*>(fw + kF_w0 + t * 8), wb = *reinterpret_cast<const float4*>(fw + kF_w0 + t * 8 + 4);
+      acc[0] = fmaf(a, wa.x, acc[0]); acc[1] = fmaf(a, wa.y, acc[1]); acc[2] = fmaf(a, wa.z, acc[2]); acc[3] = fmaf(a, wa.w, acc[3]);
+      acc[4] = fmaf(a, wb.x, acc[4]); acc[5] = fmaf(a, wb.y, acc[5]); acc[6] = fmaf(a, wb.z, acc[6]); acc[7] = fmaf(a, wb.w, acc[7]);
     }
     const int p = (r + 1) * kPW + c + 1;
     *reinterpret_cast<uint4*>(smem + OFF_A1 + (kPosGuard + p) * 16) =
@@ -100,29 +116,38 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   }
   fence_proxy_async_smem();
   __syncthreads();
+  AFT_CONV_STAMP(1);
 
   // ---- conv2 (8 -> 32) on the tensor core: 16 tiles x 9 taps, K = 16 (8 channels + 8 zero channels)
   if (warp == 0) {   // converged warp, elected lane issues (keeps the descriptor math in uniform registers)
     const bool el = elect_one();
     tc_fence_after_sync();
-    const uint32_t a1 = sb + OFF_A1 + kPosGuard * 16;
+    const uint32_t a_lo = desc_lo_none(sb + OFF_A1 + kPosGuard * 16, kPlaneBytes);   // + positions (16 B each == 1 address unit)
+    const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW2, 512);
 #pragma unroll 1
     for (int i = 0; i < kTiles; ++i)
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int shift = (t / 3 - 1) * kPW + (t % 3 - 1);
-        mma_ss(tmem + i * 32, desc_k_none(a1 + (i * 128 + shift) * 16, kPlaneBytes), desc_k_none(sb + OFF_PK + kPkW2 + t * 1024, 512),
-               kIdescConv2, t > 0, el);
+        mma_ss(tmem + i * 32, desc_join(a_lo + i * 128 + shift), desc_join(b_lo + t * 64), kIdescConv2, t > 0, el);
       }
     mma_commit(bar, el);
   }
+  AFT_CONV_STAMP(2);
   mbar_wait(bar, phase & 1);
   tc_fence_after_sync();
+  AFT_CONV_STAMP(3);
 
   // ---- conv2 epilogue: + bias, ReLU, zero the border positions -> mid planes (4 groups of 8 channels, bf16)
   {
     const int q = warp & 3, part = warp >> 2;
-#pragma unroll 1
+    float b1[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(fw + kF_b1 + j);
+      b1[j] = b.x; b1[j + 1] = b.y; b1[j + 2] = b.z; b1[j + 3] = b.w;
+    }
+#pragma unroll 2
     for (int i = part; i < kTiles; i += 4) {
       const int p = i * 128 + q * 32 + lane;
       uint32_t acc[32];
@@ -135,8 +160,8 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float v0 = fmaxf(__uint_as_float(acc[g * 8 + 2 * j]) + fw[kF_b1 + g * 8 + 2 * j], 0.f);
-          const float v1 = fmaxf(__uint_as_float(acc[g * 8 + 2 * j + 1]) + fw[kF_b1 + g * 8 + 2 * j + 1], 0.f);
+          const float v0 = fmaxf(__uint_as_float(acc[g * 8 + 2 * j]) + b1[g * 8 + 2 * j], 0.f);
+          const float v1 = fmaxf(__uint_as_float(acc[g * 8 + 2 * j + 1]) + b1[g * 8 + 2 * j + 1], 0.f);
           pk[j] = in_img ? pack_bf16x2(v0, v1) : 0u;
         }
         *reinterpret_cast<uint4*>(smem + OFF_MID + g * kPlaneBytes + (kPosGuard + p) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -146,12 +171,14 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   tc_fence_before_sync();
   fence_proxy_async_smem();
   __syncthreads();
+  AFT_CONV_STAMP(4);
 
   // ---- conv3 (32 -> 8) on the tensor core: 16 tiles x 9 taps x 2 K-steps, N = 16 (8 real + 8 zero output channels)
   if (warp == 0) {
     const bool el = elect_one();
     tc_fence_after_sync();
-    const uint32_t mid = sb + OFF_MID + kPosGuard * 16;
+    const uint32_t a_lo = desc_lo_none(sb + OFF_MID + kPosGuard * 16, kPlaneBytes);
+    const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW3, 256);
 #pragma unroll 1
     for (int i = 0; i < kTiles; ++i)
 #pragma unroll
@@ -159,13 +186,15 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
         const int shift = (t / 3 - 1) * kPW + (t % 3 - 1);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          mma_ss(tmem + i * 16, desc_k_none(mid + 2 * ks * kPlaneBytes + (i * 128 + shift) * 16, kPlaneBytes),
-                 desc_k_none(sb + OFF_PK + kPkW3 + (t * 2 + ks) * 512, 256), kIdescConv3, (t | ks) != 0, el);
+          mma_ss(tmem + i * 16, desc_join(a_lo + ks * (2 * kPlaneBytes / 16) + i * 128 + shift), desc_join(b_lo + (t * 2 + ks) * 32),
+                 kIdescConv3, (t | ks) != 0, el);
       }
     mma_commit(bar + 8, el);
   }
+  AFT_CONV_STAMP(5);
   mbar_wait(bar + 8, phase & 1);
   tc_fence_after_sync();
+  AFT_CONV_STAMP(6);
 
   // ---- conv3 epilogue: + bias, ReLU, zero borders -> a3 (bf16, reuses the a1 group-0 plane: conv2 has consumed it)
   {
@@ -189,25 +218,27 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   }
   tc_fence_before_sync();
   __syncthreads();
+  AFT_CONV_STAMP(7);
 
   // ---- conv4 (8 -> 1, no activation) on CUDA cores -> fp32 result, unpadded, at OFF_IN
   for (int px = tid; px < kPix; px += kThreads) {
     const int r = px / kGridW, c = px - r * kGridW;
-    float acc = fw[kF_b3];
+    float acc[4] = {fw[kF_b3], 0.f, 0.f, 0.f};   // four partial sums: short dependency chains
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int p = (r + t / 3) * kPW + c + t % 3;
       const uint4 a = *reinterpret_cast<const uint4*>(smem + OFF_A1 + (kPosGuard + p) * 16);
       const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc = fmaf(__uint_as_float(w[j] << 16), fw[kF_w3 + t * 8 + 2 * j], acc);
-        acc = fmaf(__uint_as_float(w[j] & 0xFFFF0000u), fw[kF_w3 + t * 8 + 2 * j + 1], acc);
-      }
+      const float4 wa = *reinterpret_cast<const float4*>(fw + kF_w3 + t * 8), wb = *reinterpret_cast<const float4*>(fw + kF_w3 + t * 8 + 4);
+      acc[0] = fmaf(__uint_as_float(w[0] << 16), wa.x, acc[0]); acc[1] = fmaf(__uint_as_float(w[0] & 0xFFFF0000u), wa.y, acc[1]);
+      acc[2] = fmaf(__uint_as_float(w[1] << 16), wa.z, acc[2]); acc[3] = fmaf(__uint_as_float(w[1] & 0xFFFF0000u), wa.w, acc[3]);
+      acc[0] = fmaf(__uint_as_float(w[2] << 16), wb.x, acc[0]); acc[1] = fmaf(__uint_as_float(w[2] & 0xFFFF0000u), wb.y, acc[1]);
+      acc[2] = fmaf(__uint_as_float(w[3] << 16), wb.z, acc[2]); acc[3] = fmaf(__uint_as_float(w[3] & 0xFFFF0000u), wb.w, acc[3]);
     }
-    reinterpret_cast<float*>(smem + OFF_OUT)[px] = acc;
+    reinterpret_cast<float*>(smem + OFF_OUT)[px] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   }
   __syncthreads();
+  AFT_CONV_STAMP(8);
 }
 
 }  // namespace convtc

@@ -46,6 +46,9 @@ namespace {
 
 using namespace ptx;
 
+#ifndef AFT_TC_POLY_EXP
+#define AFT_TC_POLY_EXP 0   // 1: one exponential in four goes through ex2_poly (FMA pipe) instead of MUFU (measured: no gain, both pipes are equally loaded)
+#endif
 #ifndef AFT_TC_PARTS
 #define AFT_TC_PARTS 4
 #endif
@@ -120,6 +123,18 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// exp2 for x <= 0 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, |f| <= 0.5 by the 1.5 * 2^23 rounding trick,
+// cubic minimax for 2^f (max rel. error 1.9e-4, 20x below the bf16 rounding of P), 2^n added straight into the exponent
+// field ((bits(t) << 23) == (n << 23) because the low 9 bits of the magic constant are zero).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05322283f, 0.2424649f);
+  p = fmaf(p, f, 0.69373846f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
@@ -280,9 +295,12 @@ __device__ __forceinline__ float softmax_load(uint32_t tmem, int q, int part, fl
 // (2) exponentials in place (scores are in log2 units: q rows of in_proj pre-scaled by log2(e)/sqrt(dh)); returns the sum
 __device__ __forceinline__ float softmax_exp(float (&v)[kSmCols], float m) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  // The exponentials are MUFU-bound (16 ex2 / clk / SM); every kPolyEvery-th one is computed on the FMA pipe instead
+  // so that both pipes finish together.
 #pragma unroll
   for (int j = 0; j < kSmCols; j += 4) {
-    v[j] = ex2(v[j] - m); v[j + 1] = ex2(v[j + 1] - m); v[j + 2] = ex2(v[j + 2] - m); v[j + 3] = ex2(v[j + 3] - m);
+    v[j] = ex2(v[j] - m); v[j + 1] = ex2(v[j + 1] - m); v[j + 2] = ex2(v[j + 2] - m);
+    v[j + 3] = AFT_TC_POLY_EXP ? ex2_poly(v[j + 3] - m) : ex2(v[j + 3] - m);
     s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3];
   }
   return (s0 + s1) + (s2 + s3);
@@ -1157,6 +1175,7 @@ bool tc_selftest(int which, double* max_err, cudaStream_t st) {
         for (int h = 0; h < 2; ++h)
           for (unsigned long long i = 1; i <= g_timeline_host[500 * h] && i < 500; ++i, ++n_ev)
             fprintf(stderr, "TL %llu %llu\n", g_timeline_host[500 * h + i] >> 48, g_timeline_host[500 * h + i] & 0xFFFFFFFFFFFFull);
+      conv_tc_dump_timeline();
       g_timeline_arm = nullptr;
       *max_err = (double)n_ev;
       return true;

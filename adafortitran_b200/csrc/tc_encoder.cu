@@ -52,6 +52,9 @@ using namespace ptx;
 #ifndef AFT_TC_PARTS
 #define AFT_TC_PARTS 4
 #endif
+#ifndef AFT_TC_TAILT
+#define AFT_TC_TAILT 1      // 1: the 24-row tail tile of every head is processed in transposed form (see "tail tile" below)
+#endif
 constexpr int kParts = AFT_TC_PARTS;   // threads per accumulator row = compute warpgroups (2: 8 warps x 224 regs, 4: 16 warps x 104 regs)
 static_assert(kParts == 2 || kParts == 4, "kParts must be 2 or 4");
 constexpr int kComputeWarps = 4 * kParts;
@@ -117,6 +120,11 @@ constexpr uint32_t kIdescS = make_idesc_bf16(128, 144, false, false);
 constexpr uint32_t kIdescPV = make_idesc_bf16(128, 32, false, true);     // B = V, MN-major
 constexpr uint32_t kIdescN128 = make_idesc_bf16(128, 128, false, false);
 constexpr uint32_t kIdescN64 = make_idesc_bf16(128, 64, false, false);
+constexpr uint32_t kIdescST = make_idesc_bf16(128, 32, false, false);   // S^T block: A = 128 keys, B = 32 tail queries
+constexpr uint32_t kIdescOT = make_idesc_bf16(128, 32, true, true);     // O^T: A = V^T (MN-major), B = P^T (MN-major)
+// Tail tile exchange arrays ([4 quadrants][32 queries] f32 each): the padding rows 280..287 of the O image, chunk 0.
+// Those rows are never written during attention by the transposed path and out_proj only turns them into padding rows.
+constexpr uint32_t OFF_XT_MAX = OFF_O + 280 * 128, OFF_XT_SUM = OFF_XT_MAX + 512;
 
 
 __device__ __forceinline__ float ex2(float x) {
@@ -227,6 +235,31 @@ __device__ __forceinline__ void issue_pv(uint32_t tmem, uint32_t sb, int obuf, b
 #pragma unroll 6
   for (int ks = 0; ks < 18; ++ks)
     mma_ts(tmem + TM_O + obuf * 32, tmem + TM_P + ks * 8, desc_mn_sw64(v + ks * 1024), kIdescPV, ks > 0, el);
+}
+
+// ---- tail tile (query rows 256..287), transposed.  TMEM lane quadrant w % 4 belongs to the warps of SM sub-partition
+// w % 4, so a 128 x 288 score tile with 32 valid rows keeps a single sub-partition (one MUFU) busy while 12 of the 16
+// compute warps wait.  Transposed, S^T = K_g . Q_tail^T puts the 288 keys on the lanes (three 128-lane blocks, N = 32
+// query columns each): every quadrant owns keys, the exponentials are spread over all four sub-partitions.  P^T is
+// written to shared memory with the layout of the V image (keys x 32, MN-major) over the dead Q image, and
+// O^T = V_g^T . P^T (A = V image read MN-major, lanes = head dim) lands in the usual O accumulator columns.
+__device__ __forceinline__ void issue_scores_tail(uint32_t tmem, uint32_t sb, bool el = true) {
+  const uint32_t k = sb + OFF_QKV + kQkvPart;
+  const uint32_t qt = sb + OFF_QKV + 256 * 64;
+#pragma unroll
+  for (int b = 0; b < 3; ++b)     // block 2 = keys 256..383: rows past 287 read the V image, their lanes are never loaded
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      mma_ss(tmem + TM_S + b * 32, desc_k_sw64(k + b * 128 * 64 + ks * 32), desc_k_sw64(qt + ks * 32), kIdescST, ks > 0, el);
+}
+__device__ __forceinline__ void issue_pv_tail(uint32_t tmem, uint32_t sb, int obuf, bool el = true) {
+  const uint32_t v = sb + OFF_QKV + 2 * kQkvPart;
+  const uint32_t pt = sb + OFF_QKV;
+  // A: M = 128 = four 32-wide MN atoms, only the first (lanes 0..31 = head dim) is meaningful; both strides of the
+  // descriptor are 512 B, so the other atoms read neighbouring key groups (in bounds, results ignored)
+#pragma unroll 6
+  for (int ks = 0; ks < 18; ++ks)
+    mma_ss(tmem + TM_O + obuf * 32, desc_mn_sw64(v + ks * 1024), desc_mn_sw64(pt + ks * 1024), kIdescOT, ks > 0, el);
 }
 
 // =============================================================================================
@@ -343,6 +376,131 @@ __device__ __forceinline__ void epi_o(uint32_t tmem, uint32_t sb, int g, int t, 
   }
 }
 
+// ---- tail tile, transposed (see issue_scores_tail)
+constexpr int kTq = 32 / kParts;   // tail queries (accumulator columns per key block) per thread
+// Column-wise reduction over the 32 lanes of a warp: N values per lane in, and on return v[0] of lane L holds the
+// reduced column L >> (5 - log2 N) (N + log2(32 / N) - 1 shuffles instead of 5 N).
+template <int N, bool kMax>
+__device__ __forceinline__ void warp_reduce_cols(float (&v)[N], int lane, int width = 16) {
+  if constexpr (N > 1) {
+    const bool upper = (lane & width) != 0;
+    float h[N / 2];
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const float send = upper ? v[i] : v[i + N / 2];
+      const float keep = upper ? v[i + N / 2] : v[i];
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, send, width);
+      h[i] = kMax ? fmaxf(keep, recv) : keep + recv;
+    }
+    warp_reduce_cols<N / 2, kMax>(h, lane, width >> 1);
+    v[0] = h[0];
+  } else {
+    for (; width >= 1; width >>= 1) {
+      const float recv = __shfl_xor_sync(0xFFFFFFFFu, v[0], width);
+      v[0] = kMax ? fmaxf(v[0], recv) : v[0] + recv;
+    }
+  }
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
+}
+// Softmax of the transposed tail tile.  Thread (q, part, lane) owns keys 128 b + 32 q + lane (b = 0, 1 and, for q = 0,
+// b = 2) and tail queries part * kTq .. + kTq.  `s_loaded` / `part_bar`: see the call site.
+__device__ __forceinline__ void softmax_tail(uint32_t tmem, uint32_t sb, uint32_t s_loaded_bar, int q, int part, int lane) {
+  const int nb = q == 0 ? 3 : 2;
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_S + part * kTq;
+  float s[3][kTq];
+  {
+    uint32_t x[3][kTq];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      if (b < nb) tmem_ld_cols(taddr + b * 32, x[b]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+      for (int j = 0; j < kTq; ++j) s[b][j] = (b < nb) ? __uint_as_float(x[b][j]) : -INFINITY;
+  }
+  if (lane >= kS - 256) {   // keys 280..287 are padding
+#pragma unroll
+    for (int j = 0; j < kTq; ++j) s[2][j] = -INFINITY;
+  }
+  tc_fence_before_sync();
+  warp_arrive(s_loaded_bar, lane);
+  const int col_shift = kTq == 8 ? 2 : 1, col = lane >> col_shift;          // column held by this lane after a reduction
+  const bool writer = (lane & ((1 << col_shift) - 1)) == 0;
+  const uint32_t xslot = (q * 32 + part * kTq + col) * 4;
+  {
+    float m[kTq];
+#pragma unroll
+    for (int j = 0; j < kTq; ++j) m[j] = fmaxf(fmaxf(s[0][j], s[1][j]), s[2][j]);
+    warp_reduce_cols<kTq, true>(m, lane);
+    if (writer) st_shared_f32(sb + OFF_XT_MAX + xslot, m[0]);
+  }
+  named_bar_sync(5 + part, 128);   // the four quadrant warps that share these query columns
+  float sum[kTq];
+#pragma unroll
+  for (int u = 0; u < kTq / 4; ++u) {
+    float4 m4 = lds_f4(sb + OFF_XT_MAX + (part * kTq + u * 4) * 4);
+#pragma unroll
+    for (int qq = 1; qq < 4; ++qq) {
+      const float4 o = lds_f4(sb + OFF_XT_MAX + (qq * 32 + part * kTq + u * 4) * 4);
+      m4.x = fmaxf(m4.x, o.x); m4.y = fmaxf(m4.y, o.y); m4.z = fmaxf(m4.z, o.z); m4.w = fmaxf(m4.w, o.w);
+    }
+    const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = u * 4 + jj;
+      float acc = 0.f;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        if (b < nb) { s[b][j] = ex2(s[b][j] - mm[jj]); acc += s[b][j]; }
+      }
+      sum[j] = acc;
+    }
+  }
+  // P^T rows (keys) -> the dead Q image, V-image layout: 64-byte rows, SWIZZLE_64B
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    if (b < nb) {
+      const int kr = b * 128 + q * 32 + lane;
+#pragma unroll
+      for (int u = 0; u < kTq / 8; ++u)
+        st_shared_v4(sb + OFF_QKV + kr * 64 + (((part * (kTq / 8) + u) ^ ((kr >> 1) & 3)) << 4),
+                     pack_bf16x2(s[b][8 * u], s[b][8 * u + 1]), pack_bf16x2(s[b][8 * u + 2], s[b][8 * u + 3]),
+                     pack_bf16x2(s[b][8 * u + 4], s[b][8 * u + 5]), pack_bf16x2(s[b][8 * u + 6], s[b][8 * u + 7]));
+    }
+  }
+  warp_reduce_cols<kTq, false>(sum, lane);
+  if (writer) st_shared_f32(sb + OFF_XT_SUM + xslot, sum[0]);
+}
+// O^T accumulator (lanes = head dim, columns = tail queries) -> / l -> bf16 -> O image rows 256..279 (quadrant 0 only)
+__device__ __forceinline__ void epi_o_tail(uint32_t tmem, uint32_t sb, int g, int obuf, int part, int lane) {
+  uint32_t a[kTq];
+  tmem_ld_cols(tmem + TM_O + obuf * 32 + part * kTq, a);
+  tmem_wait_ld();
+  const uint32_t colbyte = (uint32_t)(lane & 7) * 2;
+  const int u = (g & 1) * 4 + (lane >> 3);
+#pragma unroll
+  for (int v4 = 0; v4 < kTq / 4; ++v4) {
+    float4 l4 = lds_f4(sb + OFF_XT_SUM + (part * kTq + v4 * 4) * 4);
+#pragma unroll
+    for (int qq = 1; qq < 4; ++qq) {
+      const float4 o = lds_f4(sb + OFF_XT_SUM + (qq * 32 + part * kTq + v4 * 4) * 4);
+      l4.x += o.x; l4.y += o.y; l4.z += o.z; l4.w += o.w;
+    }
+    const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = v4 * 4 + jj, r = 256 + part * kTq + j;
+      if (r < kS) {   // rows 280..287 hold the exchange arrays
+        const float o = __uint_as_float(a[j]) * rcp_approx(ll[jj]);
+        st_shared_u16(sb + OFF_O + (g >> 1) * kXChunkBytes + r * 128 + ((u ^ (r & 7)) << 4) + colbyte, pack_bf16x2(o, 0.f));
+      }
+    }
+  }
+}
+
 // out_proj / linear2 accumulators (tile t) + bias + residual (X image) -> LayerNorm -> X image in place (+ fp32 rows to
 // h_out after the last layer).  A row is shared by the kParts threads that own TMEM lane `rt`; sum and sum of squares are
 // combined through shared memory (one exchange, one named barrier of the quadrant's warps).
@@ -402,8 +560,11 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec,
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[u * 8 + j], rstd, shift), gg[j], ee[j]);
-    st_shared_v4(xrow + (((u0 + u) ^ (r & 7)) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                 pack_bf16x2(o[6], o[7]));
+    // padding rows 280..287 stay zero: their accumulators are fed by padding rows of the O image (exchange scratch of
+    // the tail tile) and must not leak non-finite values into the V image of the next layer
+    if (r < kS)
+      st_shared_v4(xrow + (((u0 + u) ^ (r & 7)) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                   pack_bf16x2(o[6], o[7]));
     if (h_out_seq != nullptr && r < kS) {
       float4* dst = reinterpret_cast<float4*>(h_out_seq + r * kD + c0 + u * 8);
       dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -592,7 +753,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               s_loaded.wait(misc + MB_S_LOADED);      // S(t) is in registers
               tc_fence_after_sync();
               tl_event(p, tl, 130 + t, tl_n);   // S_LOADED(t) seen
+#if AFT_TC_TAILT
+              if (t == 0) { issue_scores(tmem, sb, 1, el); mma_commit(misc + MB_S_DONE, el); }
+              else if (t == 1) { issue_scores_tail(tmem, sb, el); mma_commit(misc + MB_S_DONE, el); }
+#else
               if (t < 2) { issue_scores(tmem, sb, t + 1, el); mma_commit(misc + MB_S_DONE, el); }
+#endif
               // the S columns are free after the last tile: the next head's projection runs under this tile's exponentials
               // (it only reads X and the weight slot; the Q/K/V images are rewritten later, by the epilogue)
               else if (g < 3) issue_qkv(g + 1);
@@ -601,7 +767,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               if (n_pv >= 2) mbar_wait(misc + MB_O_FREE + 8 * (n_pv & 1), ((n_pv >> 1) - 1) & 1);
               tc_fence_after_sync();
               tl_event(p, tl, 140 + t, tl_n);   // P_READY(t) seen, P.V(t) issue start
+#if AFT_TC_TAILT
+              if (t == 2) issue_pv_tail(tmem, sb, n_pv & 1, el); else issue_pv(tmem, sb, n_pv & 1, el);
+#else
               issue_pv(tmem, sb, n_pv & 1, el);
+#endif
               mma_commit(misc + MB_PV_DONE, el);
               tl_event(p, tl, 150 + t, tl_n);   // P.V(t) issued
               if (g == 3 && t == 2) mma_commit(misc + MB_ATTN_DONE, el);
@@ -707,6 +877,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           warp_arrive(misc + MB_QKV_READY, lane);
           tl_event(p, tl, 220 + g, tl_n);   // QKV epilogue done
           // ---- softmax tiles; the O epilogue of tile t-1 runs after P(t) has been handed to the tensor core
+#if AFT_TC_TAILT
+          float inv_prev = 0.f;
+#pragma unroll 1
+          for (int t = 0; t < 4; ++t) {
+            if (t < 2) {
+              mbar_wait(misc + MB_S_DONE, (n_head + t) & 1);
+              tc_fence_after_sync();
+              tl_event(p, tl, 230 + t, tl_n);   // S_DONE(t) seen
+              // the score row lives in registers from here to the P store: defined and consumed inside one block
+              float v[kSmCols];
+              float m = softmax_load(tmem, q, part, v);
+              st_shared_f32(xmax_row + part * 512, m);
+              tc_fence_before_sync();
+              warp_arrive(misc + MB_S_LOADED, lane);
+              tl_event(p, tl, 240 + t, tl_n);   // S(t) loaded
+              named_bar_sync(1 + q, 32 * kParts);                          // exchange the partial row maxima
+#pragma unroll
+              for (int pp = 0; pp < kParts; ++pp) m = fmaxf(m, ld_shared_f32(xmax_row + pp * 512));
+              const float sum = softmax_exp(v, m);
+              tl_event(p, tl, 250 + t, tl_n);   // exponentials done
+              if (t > 0) { mbar_wait(misc + MB_PV_DONE, (n_head + t - 1) & 1); tc_fence_after_sync(); }   // P.V(t-1) has consumed P
+              tl_event(p, tl, 260 + t, tl_n);   // PV_DONE(t-1) seen
+              softmax_store(tmem, q, part, v);
+              st_shared_f32(xsum_row + part * 512, sum);
+              tc_fence_before_sync();
+              warp_arrive(misc + MB_P_READY, lane);
+              tl_event(p, tl, 270 + t, tl_n);   // P(t) stored
+            } else if (t == 2) {
+              mbar_wait(misc + MB_S_DONE, (n_head + 2) & 1);
+              tc_fence_after_sync();
+              tl_event(p, tl, 232, tl_n);       // S^T seen
+              softmax_tail(tmem, sb, misc + MB_S_LOADED, q, part, lane);
+              fence_proxy_async_smem();         // P^T is read by the tensor core
+              // P.V(1) (long finished): waited for before the arrival so that the PV_DONE barrier can never run two
+              // phases ahead of a waiter; its O accumulator is read out right below
+              mbar_wait(misc + MB_PV_DONE, (n_head + 1) & 1);
+              tc_fence_after_sync();
+              warp_arrive(misc + MB_P_READY, lane);
+              tl_event(p, tl, 272, tl_n);       // P^T stored
+            } else {
+              mbar_wait(misc + MB_PV_DONE, (n_head + 2) & 1);
+              tc_fence_after_sync();
+            }
+            if (t > 0) {
+              if (t < 3) epi_o(tmem, sb, g, t - 1, (n_head + t - 1) & 1, inv_prev, q, part, lane);
+              else if (q == 0) epi_o_tail(tmem, sb, g, (n_head + 2) & 1, part, lane);
+              tc_fence_before_sync();
+              fence_proxy_async_smem();
+              warp_arrive(misc + MB_O_FREE + 8 * ((n_head + t - 1) & 1), lane);
+            }
+            if (t < 2) {
+              named_bar_sync(1 + q, 32 * kParts);                          // exchange the partial row sums
+              float l_row = 0.f;
+#pragma unroll
+              for (int pp = 0; pp < kParts; ++pp) l_row += ld_shared_f32(xsum_row + pp * 512);
+              inv_prev = rcp_approx(l_row);
+            }
+          }
+        }
+#else
           float inv_prev = 0.f;
 #pragma unroll 1
           for (int t = 0; t < 4; ++t) {
@@ -763,6 +993,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             }
           }
         }
+#endif
         // ---- out_proj epilogue: + bias + residual -> LayerNorm1 -> X
         tl_event(p, tl, 280, tl_n);   // waiting OUT_DONE
         mbar_wait(misc + MB_VEC_FULL, n_layer & 1);   // this layer's bias / LayerNorm vectors are in shared memory
@@ -1120,6 +1351,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_attn_kernel(const char
   if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
+// which = 3: the transposed tail tile (query rows 256..287) with the production helpers: S^T = K Q_tail^T, softmax over
+// the lanes, P^T -> Q image, O^T = V^T P^T, transposed store into the O image (head 0)
+__global__ void __launch_bounds__(kTcThreads, 1) selftest_tail_kernel(const char* qkv_img, float* s_out, float* o_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sb = smem_u32(smem_raw);
+  if ((sb & 1023u) != 0) __trap();
+  const uint32_t misc = sb + OFF_MISC + MISC_BARS, miscb = sb + OFF_MISC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(misc + MB_X_FULL, 1); mbar_init(misc + MB_S_DONE, 1); mbar_init(misc + MB_PV_DONE, 1);
+    mbar_init(misc + MB_P_READY, kComputeWarps); mbar_init(misc + MB_S_LOADED, kComputeWarps);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) { tmem_alloc(miscb + MISC_TMEM_PTR, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(miscb + MISC_TMEM_PTR));
+  __syncthreads();
+  if (warp >= kComputeWarps) {
+    setmaxnreg_dec<kRegsCtrl>();
+    if (warp == kMmaWarp && lane == 0) {
+      mbar_arrive_expect_tx(misc + MB_X_FULL, 3 * kQkvPart);
+      bulk_g2s(sb + OFF_QKV, qkv_img, 3 * kQkvPart, misc + MB_X_FULL);
+      mbar_wait(misc + MB_X_FULL, 0);
+      tc_fence_after_sync();
+      issue_scores_tail(tmem, sb);
+      mma_commit(misc + MB_S_DONE);
+      mbar_wait(misc + MB_P_READY, 0);
+      tc_fence_after_sync();
+      issue_pv_tail(tmem, sb, 1);
+      mma_commit(misc + MB_PV_DONE);
+    }
+  } else {
+    setmaxnreg_inc<kRegsCompute>();
+    const int q = warp & 3, part = warp >> 2;
+    mbar_wait(misc + MB_S_DONE, 0);
+    tc_fence_after_sync();
+    for (int b = 0; b < (q == 0 ? 3 : 2); ++b) {   // raw scores
+      uint32_t x[kTq];
+      tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_S + b * 32 + part * kTq, x);
+      tmem_wait_ld();
+      const int key = b * 128 + q * 32 + lane;
+      if (key < kSPad)
+        for (int j = 0; j < kTq; ++j) s_out[key * 32 + part * kTq + j] = __uint_as_float(x[j]);
+    }
+    softmax_tail(tmem, sb, misc + MB_S_LOADED, q, part, lane);
+    fence_proxy_async_smem();
+    warp_arrive(misc + MB_P_READY, lane);
+    mbar_wait(misc + MB_PV_DONE, 0);
+    tc_fence_after_sync();
+    if (q == 0) epi_o_tail(tmem, sb, 0, 1, part, lane);
+    named_bar_sync(9, 32 * kComputeWarps);
+    for (int i = threadIdx.x; i < 24 * 32; i += 32 * kComputeWarps) {
+      const int r = 256 + i / 32, c = i % 32;
+      unsigned short h;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(sb + OFF_O + r * 128 + (((c >> 3) ^ (r & 7)) << 4) + (c & 7) * 2));
+      o_out[i] = __uint_as_float((uint32_t)h << 16);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
+}
+
 float bf16_round_host(float x) {
   uint32_t u;
   memcpy(&u, &x, 4);
@@ -1292,6 +1589,64 @@ bool tc_selftest(int which, double* max_err, cudaStream_t st) {
     // scores must be exact to fp32 accumulation; outputs carry the bf16 rounding of P (~2^-9 relative)
     *max_err = fmax(worst_s, worst_o);
     if (worst_s > 1e-3) { set_error("selftest attn tile %d: scores off by %g (outputs %g)", tile, worst_s, worst_o); }
+    return true;
+  }
+  if (which == 3) {
+    std::vector<float> Q(288 * 32), K(288 * 32), V(288 * 32);
+    for (auto& v : Q) v = bf16_round_host(rng.next() * 1.5f);
+    for (auto& v : K) v = bf16_round_host(rng.next() * 1.5f);
+    for (auto& v : V) v = bf16_round_host(rng.next());
+    std::vector<uint16_t> img(3 * kQkvPart / 2, 0);
+    auto put = [&](int part, const std::vector<float>& M) {
+      for (int r = 0; r < 288; ++r)
+        for (int c = 0; c < 32; ++c) {
+          const int u = c >> 3, sw = (r >> 1) & 3;
+          img[(part * kQkvPart + r * 64 + ((u ^ sw) << 4)) / 2 + (c & 7)] = bf16_bits_host(M[r * 32 + c]);
+        }
+    };
+    put(0, Q); put(1, K); put(2, V);
+    char* di = nullptr;
+    float *ds = nullptr, *dO = nullptr;
+    if (cudaMalloc(&di, 3 * kQkvPart) != cudaSuccess || cudaMalloc(&ds, 288 * 32 * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&dO, 24 * 32 * sizeof(float)) != cudaSuccess) {
+      set_error("selftest: cudaMalloc failed");
+      return false;
+    }
+    cudaMemsetAsync(ds, 0, 288 * 32 * sizeof(float), st);
+    cudaMemsetAsync(dO, 0, 24 * 32 * sizeof(float), st);
+    cudaMemcpyAsync(di, img.data(), 3 * kQkvPart, cudaMemcpyHostToDevice, st);
+    cudaFuncSetAttribute(selftest_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    selftest_tail_kernel<<<1, kTcThreads, kTcSmemBytes, st>>>(di, ds, dO);
+    count_launch();
+    std::vector<float> S(288 * 32), O(24 * 32);
+    cudaMemcpyAsync(S.data(), ds, S.size() * sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(O.data(), dO, O.size() * sizeof(float), cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(di); cudaFree(ds); cudaFree(dO);
+    if (e != cudaSuccess) { set_error("selftest tail: %s", cudaGetErrorString(e)); return false; }
+    double worst_s = 0.0, worst_o = 0.0;
+    for (int i = 0; i < 24; ++i) {
+      const int qi = 256 + i;
+      std::vector<double> sc(280);
+      double mx = -1e30;
+      for (int j = 0; j < 280; ++j) {
+        double acc = 0.0;
+        for (int c = 0; c < 32; ++c) acc += (double)Q[qi * 32 + c] * (double)K[j * 32 + c];
+        sc[j] = acc;
+        mx = fmax(mx, acc);
+        worst_s = fmax(worst_s, fabs(acc - (double)S[j * 32 + i]));
+      }
+      double l = 0.0;
+      std::vector<double> o(32, 0.0);
+      for (int j = 0; j < 280; ++j) {
+        const double pj = exp2(sc[j] - mx);
+        l += pj;
+        for (int c = 0; c < 32; ++c) o[c] += pj * (double)V[j * 32 + c];
+      }
+      for (int c = 0; c < 32; ++c) worst_o = fmax(worst_o, fabs(o[c] / l - (double)O[i * 32 + c]));
+    }
+    *max_err = fmax(worst_s, worst_o);
+    if (worst_s > 1e-3 || worst_o > 2e-2) set_error("selftest tail: scores off by %g, outputs off by %g", worst_s, worst_o);
     return true;
   }
   set_error("aft_selftest: unknown test %d", which);

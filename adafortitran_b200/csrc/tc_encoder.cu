@@ -52,6 +52,9 @@ using namespace ptx;
 #ifndef AFT_TC_PARTS
 #define AFT_TC_PARTS 4
 #endif
+#ifndef AFT_TC_GELU_TANH
+#define AFT_TC_GELU_TANH 1  // 1: GELU through one MUFU.TANH (erf-fitted odd polynomial argument), 0: erf by Abramowitz-Stegun (2 MUFU)
+#endif
 #ifndef AFT_TC_TAILT
 #define AFT_TC_TAILT 1      // 1: the 24-row tail tile of every head is processed in transposed form (see "tail tile" below)
 #endif
@@ -162,6 +165,17 @@ __device__ __forceinline__ float gelu_fast(float x) {
   p = fmaf(p, t, 0.5f * 0.254829592f);
   const float y = p * t * e;
   return fmaf(-ax, y, fmaxf(x, 0.f));
+}
+// GELU(x) = x Phi(x) with Phi(x) ~ 0.5 (1 + tanh(x (a + b x^2 + c x^4))), coefficients fitted to the erf form
+// (max |error| 2.5e-5 over the real line, plus the 2^-11 relative error of MUFU.TANH: |x| 2.4e-4 at most, i.e. at or
+// below the bf16 rounding of the hidden activations it feeds).  One MUFU and six FMA-pipe operations per element.
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, fmaf(x2, -3.51516789e-4f, 3.70056460e-2f), 7.97507884e-1f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 __device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
   lo = __uint_as_float(w << 16);
@@ -336,6 +350,38 @@ __device__ __forceinline__ float softmax_exp(float (&v)[kSmCols], float m) {
     v[j + 3] = AFT_TC_POLY_EXP ? ex2_poly(v[j + 3] - m) : ex2(v[j + 3] - m);
     s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3];
   }
+  return (s0 + s1) + (s2 + s3);
+}
+// (2+3) exponentials and P store interleaved (16 columns at a time): the packing and the TMEM stores issue under the
+// MUFU-bound exponentials instead of after them.  The caller has made sure that P.V(t-1) no longer reads P.
+__device__ __forceinline__ float softmax_exp_store(uint32_t tmem, int q, int part, float (&v)[kSmCols], float m) {
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_P + part * (kSmCols / 2);
+  constexpr int kFull = kSmCols / 16;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kFull; ++i) {
+#pragma unroll
+    for (int j = i * 16; j < i * 16 + 16; j += 4) {
+      v[j] = ex2(v[j] - m); v[j + 1] = ex2(v[j + 1] - m); v[j + 2] = ex2(v[j + 2] - m); v[j + 3] = ex2(v[j + 3] - m);
+      s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3];
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[i * 16 + 2 * j], v[i * 16 + 2 * j + 1]);
+    tmem_st8(taddr + i * 8, pk);
+  }
+  if (kSmCols % 16) {
+#pragma unroll
+    for (int j = kFull * 16; j < kSmCols; j += 4) {
+      v[j] = ex2(v[j] - m); v[j + 1] = ex2(v[j + 1] - m); v[j + 2] = ex2(v[j + 2] - m); v[j + 3] = ex2(v[j + 3] - m);
+      s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3];
+    }
+    uint32_t pk4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pk4[j] = pack_bf16x2(v[kFull * 16 + 2 * j], v[kFull * 16 + 2 * j + 1]);
+    tmem_st4(taddr + kFull * 8, pk4);
+  }
+  tmem_wait_st();
   return (s0 + s1) + (s2 + s3);
 }
 // (3) P tile -> TMEM as bf16 pairs (A operand of P.V): kSmCols / 2 packed columns per thread
@@ -594,7 +640,7 @@ __device__ __forceinline__ void act_store(uint32_t sb, int c, int t, int act, in
   const int r = t * 128 + q * 32 + lane;
   if (act == AFT_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < kActCols; ++j) f[j] = gelu_fast(f[j]);
+    for (int j = 0; j < kActCols; ++j) f[j] = AFT_TC_GELU_TANH ? gelu_tanh(f[j]) : gelu_fast(f[j]);
   } else {
 #pragma unroll
     for (int j = 0; j < kActCols; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -895,11 +941,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               named_bar_sync(1 + q, 32 * kParts);                          // exchange the partial row maxima
 #pragma unroll
               for (int pp = 0; pp < kParts; ++pp) m = fmaxf(m, ld_shared_f32(xmax_row + pp * 512));
-              const float sum = softmax_exp(v, m);
-              tl_event(p, tl, 250 + t, tl_n);   // exponentials done
-              if (t > 0) { mbar_wait(misc + MB_PV_DONE, (n_head + t - 1) & 1); tc_fence_after_sync(); }   // P.V(t-1) has consumed P
+              // P.V(t-1) was issued a score load ago: it has all but always consumed P by now
+              if (t > 0) { mbar_wait(misc + MB_PV_DONE, (n_head + t - 1) & 1); tc_fence_after_sync(); }
               tl_event(p, tl, 260 + t, tl_n);   // PV_DONE(t-1) seen
-              softmax_store(tmem, q, part, v);
+              const float sum = softmax_exp_store(tmem, q, part, v, m);
+              tl_event(p, tl, 250 + t, tl_n);   // exponentials done, P stored
               st_shared_f32(xsum_row + part * 512, sum);
               tc_fence_before_sync();
               warp_arrive(misc + MB_P_READY, lane);

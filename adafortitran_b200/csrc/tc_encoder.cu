@@ -233,22 +233,28 @@ __device__ __forceinline__ void issue_gemm_sw128(uint32_t tmem, uint32_t d_col, 
     mma_ss(tmem + d_col, ((uint64_t)kHi << 32) | a, ((uint64_t)kHi << 32) | b, idesc, accumulate_first || ks > 0, el);
   }
 }
+// Descriptors of the attention operands: constant high word (SBO | version | swizzle), low word = LBO | address >> 4,
+// so that stepping through an operand is one 32-bit add per MMA.
+constexpr uint32_t kDescHiSw64 = (uint32_t)(((uint64_t)(512 >> 4)) | ((uint64_t)1 << 14) | ((uint64_t)kSwizzle64 << 29));
+__device__ __forceinline__ uint32_t desc_lo_k64(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | ((16u >> 4) << 16); }     // K-major, LBO 16
+__device__ __forceinline__ uint32_t desc_lo_mn64(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | ((512u >> 4) << 16); }   // MN-major, LBO 512
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t lo) { return ((uint64_t)kDescHiSw64 << 32) | lo; }
 // S[tile t] = Q_g[tile t] . K_g^T   (two N = 144 halves, K = 32)
 __device__ __forceinline__ void issue_scores(uint32_t tmem, uint32_t sb, int t, bool el = true) {
-  const uint32_t q = sb + OFF_QKV + t * 128 * 64;
-  const uint32_t k = sb + OFF_QKV + kQkvPart;
+  const uint32_t q = desc_lo_k64(sb + OFF_QKV + t * 128 * 64);
+  const uint32_t k = desc_lo_k64(sb + OFF_QKV + kQkvPart);
 #pragma unroll
   for (int nh = 0; nh < 2; ++nh)
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
-      mma_ss(tmem + TM_S + nh * 144, desc_k_sw64(q + ks * 32), desc_k_sw64(k + nh * 144 * 64 + ks * 32), kIdescS, ks > 0, el);
+      mma_ss(tmem + TM_S + nh * 144, desc_sw64(q + ks * 2), desc_sw64(k + (nh * 144 * 64) / 16 + ks * 2), kIdescS, ks > 0, el);
 }
 // O_acc[buf] = P (TMEM, bf16 pairs) . V_g   (K = 288 keys = 18 steps, N = 32)
 __device__ __forceinline__ void issue_pv(uint32_t tmem, uint32_t sb, int obuf, bool el = true) {
-  const uint32_t v = sb + OFF_QKV + 2 * kQkvPart;
-#pragma unroll 6
-  for (int ks = 0; ks < 18; ++ks)
-    mma_ts(tmem + TM_O + obuf * 32, tmem + TM_P + ks * 8, desc_mn_sw64(v + ks * 1024), kIdescPV, ks > 0, el);
+  const uint32_t v = desc_lo_mn64(sb + OFF_QKV + 2 * kQkvPart);
+  const uint32_t d = tmem + TM_O + obuf * 32, a = tmem + TM_P;
+#pragma unroll
+  for (int ks = 0; ks < 18; ++ks) mma_ts(d, a + ks * 8, desc_sw64(v + ks * 64), kIdescPV, ks > 0, el);
 }
 
 // ---- tail tile (query rows 256..287), transposed.  TMEM lane quadrant w % 4 belongs to the warps of SM sub-partition
@@ -258,22 +264,22 @@ __device__ __forceinline__ void issue_pv(uint32_t tmem, uint32_t sb, int obuf, b
 // written to shared memory with the layout of the V image (keys x 32, MN-major) over the dead Q image, and
 // O^T = V_g^T . P^T (A = V image read MN-major, lanes = head dim) lands in the usual O accumulator columns.
 __device__ __forceinline__ void issue_scores_tail(uint32_t tmem, uint32_t sb, bool el = true) {
-  const uint32_t k = sb + OFF_QKV + kQkvPart;
-  const uint32_t qt = sb + OFF_QKV + 256 * 64;
+  const uint32_t k = desc_lo_k64(sb + OFF_QKV + kQkvPart);
+  const uint32_t qt = desc_lo_k64(sb + OFF_QKV + 256 * 64);
 #pragma unroll
   for (int b = 0; b < 3; ++b)     // block 2 = keys 256..383: rows past 287 read the V image, their lanes are never loaded
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
-      mma_ss(tmem + TM_S + b * 32, desc_k_sw64(k + b * 128 * 64 + ks * 32), desc_k_sw64(qt + ks * 32), kIdescST, ks > 0, el);
+      mma_ss(tmem + TM_S + b * 32, desc_sw64(k + (b * 128 * 64) / 16 + ks * 2), desc_sw64(qt + ks * 2), kIdescST, ks > 0, el);
 }
 __device__ __forceinline__ void issue_pv_tail(uint32_t tmem, uint32_t sb, int obuf, bool el = true) {
-  const uint32_t v = sb + OFF_QKV + 2 * kQkvPart;
-  const uint32_t pt = sb + OFF_QKV;
+  const uint32_t v = desc_lo_mn64(sb + OFF_QKV + 2 * kQkvPart);
+  const uint32_t pt = desc_lo_mn64(sb + OFF_QKV);
+  const uint32_t d = tmem + TM_O + obuf * 32;
   // A: M = 128 = four 32-wide MN atoms, only the first (lanes 0..31 = head dim) is meaningful; both strides of the
   // descriptor are 512 B, so the other atoms read neighbouring key groups (in bounds, results ignored)
-#pragma unroll 6
-  for (int ks = 0; ks < 18; ++ks)
-    mma_ss(tmem + TM_O + obuf * 32, desc_mn_sw64(v + ks * 1024), desc_mn_sw64(pt + ks * 1024), kIdescOT, ks > 0, el);
+#pragma unroll
+  for (int ks = 0; ks < 18; ++ks) mma_ss(d, desc_sw64(v + ks * 64), desc_sw64(pt + ks * 64), kIdescOT, ks > 0, el);
 }
 
 // =============================================================================================
@@ -296,13 +302,27 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {   // 16-byte shared lo
 // QKV accumulators of (head g, row tile t) -> + bias -> bf16 -> Q_g / K_g / V_g images (SWIZZLE_64B rows of 64 B).
 // The 96 accumulator columns [q_g | k_g | v_g] = 12 units of 8 columns, split evenly over the warpgroups.
 constexpr int kQkvUnits = 12 / kParts;
+__device__ __forceinline__ void epi_qkv_store(uint32_t sb, uint32_t bias96, int t, int q, int part, int lane, const uint32_t (&acc)[8 * kQkvUnits]);
 __device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, uint32_t bias96, int t, int q, int part, int lane) {
-  const int r = t * 128 + q * 32 + lane;
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + t * 96 + part * (8 * kQkvUnits);
-  const int sw = (r >> 1) & 3;
   uint32_t acc[8 * kQkvUnits];
   tmem_ld_cols(taddr, acc);
   tmem_wait_ld();
+  epi_qkv_store(sb, bias96, t, q, part, lane, acc);
+}
+// row tiles 0 and 1 together: one TMEM round trip instead of two
+__device__ __forceinline__ void epi_qkv_pair(uint32_t tmem, uint32_t sb, uint32_t bias96, int q, int part, int lane) {
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + part * (8 * kQkvUnits);
+  uint32_t acc0[8 * kQkvUnits], acc1[8 * kQkvUnits];
+  tmem_ld_cols(taddr, acc0);
+  tmem_ld_cols(taddr + 96, acc1);
+  tmem_wait_ld();
+  epi_qkv_store(sb, bias96, 0, q, part, lane, acc0);
+  epi_qkv_store(sb, bias96, 1, q, part, lane, acc1);
+}
+__device__ __forceinline__ void epi_qkv_store(uint32_t sb, uint32_t bias96, int t, int q, int part, int lane, const uint32_t (&acc)[8 * kQkvUnits]) {
+  const int r = t * 128 + q * 32 + lane;
+  const int sw = (r >> 1) & 3;
 #pragma unroll
   for (int i = 0; i < kQkvUnits; ++i) {
     const int u8 = part * kQkvUnits + i;     // unit index inside [q | k | v]
@@ -776,18 +796,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           // X and the accumulator columns [0,384) are free once the previous LayerNorm2 has finished
           if (n_layers_done > 0) x2_ready.wait(misc + MB_X2_READY);
           tc_fence_after_sync();
-          auto issue_qkv = [&](int g) {   // QKV projection of head g, three row tiles; accumulators alias the S columns
-            mbar_wait(misc + MB_W_FULL, n_in & 1);
-            tc_fence_after_sync();
-            tl_event(p, tl, 100 + g, tl_n);   // QKV(g) issue start
-            for (int t = 0; t < 3; ++t)
+          // QKV projection of head g, row tiles [t0, t1); accumulators alias the S columns.  `first` waits for the weight
+          // slice, `last` releases it and publishes the accumulators.
+          auto issue_qkv = [&](int g, int t0, int t1, bool first, bool last) {
+            if (first) {
+              mbar_wait(misc + MB_W_FULL, n_in & 1);
+              tc_fence_after_sync();
+              tl_event(p, tl, 100 + g, tl_n);   // QKV(g) issue start
+            }
+            for (int t = t0; t < t1; ++t)
               issue_gemm_sw128(tmem, TM_QKV + t * 96, sb + OFF_X + t * 128 * 128, kXChunkBytes, sb + OFF_W, 96 * 128, 8, kIdescQkv, false, el);
-            mma_commit(misc + MB_W_EMPTY, el);
-            mma_commit(misc + MB_QKV_DONE, el);
-            tl_event(p, tl, 110 + g, tl_n);   // QKV(g) issued
-            ++n_in;
+            if (last) {
+              mma_commit(misc + MB_W_EMPTY, el);
+              mma_commit(misc + MB_QKV_DONE, el);
+              tl_event(p, tl, 110 + g, tl_n);   // QKV(g) issued
+              ++n_in;
+            }
           };
-          issue_qkv(0);
+          issue_qkv(0, 0, 3, true, true);
           for (int g = 0; g < 4; ++g) {
             // ---- attention of head g
             qkv_ready.wait(misc + MB_QKV_READY);
@@ -801,13 +827,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               tl_event(p, tl, 130 + t, tl_n);   // S_LOADED(t) seen
 #if AFT_TC_TAILT
               if (t == 0) { issue_scores(tmem, sb, 1, el); mma_commit(misc + MB_S_DONE, el); }
-              else if (t == 1) { issue_scores_tail(tmem, sb, el); mma_commit(misc + MB_S_DONE, el); }
+              else if (t == 1) {
+                issue_scores_tail(tmem, sb, el);
+                mma_commit(misc + MB_S_DONE, el);
+                // S^T only occupies columns [0, 96): row tiles 1 and 2 of the next head's projection start right away
+                if (g < 3) issue_qkv(g + 1, 1, 3, true, false);
+              }
+              else if (g < 3) issue_qkv(g + 1, 0, 1, false, true);
 #else
-              if (t < 2) { issue_scores(tmem, sb, t + 1, el); mma_commit(misc + MB_S_DONE, el); }
-#endif
               // the S columns are free after the last tile: the next head's projection runs under this tile's exponentials
               // (it only reads X and the weight slot; the Q/K/V images are rewritten later, by the epilogue)
-              else if (g < 3) issue_qkv(g + 1);
+              if (t < 2) { issue_scores(tmem, sb, t + 1, el); mma_commit(misc + MB_S_DONE, el); }
+              else if (g < 3) issue_qkv(g + 1, 0, 3, true, true);
+#endif
               p_ready.wait(misc + MB_P_READY);         // P(t) is in TMEM
               // O accumulator n_pv & 1 was last used by P.V #(n_pv - 2): its epilogue must have read it out
               if (n_pv >= 2) mbar_wait(misc + MB_O_FREE + 8 * (n_pv & 1), ((n_pv >> 1) - 1) & 1);
@@ -858,8 +890,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               mma_commit(misc + MB_F1_DONE + 8 * buf, el);
               tl_event(p, tl, 180 + 3 * c + t, tl_n);   // FFN1(c,t) issued
               if (t == 2) ring_release(ring_base + 2 + 2 * c);
-              if (t == 0 && c > 0) {
-                // FFN2 partial of the previous chunk (its hidden image is complete by now or soon)
+              if (t == 1 && c > 0) {
+                // FFN2 partial of the previous chunk, after both FFN1 buffers have been refilled: the GELU warps find
+                // the next accumulator tile ready instead of waiting behind these twelve MMAs
                 tl_event(p, tl, 192, tl_n);   // waiting HID_READY
                 hid_ready.wait(misc + MB_HID_READY);
                 tc_fence_after_sync();
@@ -915,9 +948,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           tc_fence_after_sync();
           mbar_wait(misc + MB_BIAS_FULL + 8 * (g & 1), (n_head >> 1) & 1);   // in_proj bias of this head (buffer g & 1)
           tl_event(p, tl, 210 + g, tl_n);   // QKV_DONE seen
-#pragma unroll 1
-          for (int t = 0; t < 3; ++t)
-            if (t < 2 || tile2_active) epi_qkv(tmem, sb, qkv_bias + (g & 1) * kQkvBiasBytes, t, q, part, lane);
+          epi_qkv_pair(tmem, sb, qkv_bias + (g & 1) * kQkvBiasBytes, q, part, lane);
+          if (tile2_active) epi_qkv(tmem, sb, qkv_bias + (g & 1) * kQkvBiasBytes, 2, q, part, lane);
           tc_fence_before_sync();
           fence_proxy_async_smem();
           warp_arrive(misc + MB_QKV_READY, lane);

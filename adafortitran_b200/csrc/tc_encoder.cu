@@ -128,6 +128,10 @@ constexpr uint32_t kIdescOT = make_idesc_bf16(128, 32, true, true);     // O^T: 
 // Tail tile exchange arrays ([4 quadrants][32 queries] f32 each): the padding rows 280..287 of the O image, chunk 0.
 // Those rows are never written during attention by the transposed path and out_proj only turns them into padding rows.
 constexpr uint32_t OFF_XT_MAX = OFF_O + 280 * 128, OFF_XT_SUM = OFF_XT_MAX + 512;
+// Second LayerNorm exchange area (2 x kXchgArray bytes), used by row tile 1: the start of the O region.  Both LayerNorms run
+// when that region is dead (O image consumed by out_proj / hidden images consumed by FFN2, next writer behind a full
+// X1_READY / X2_READY hand-shake).
+constexpr uint32_t OFF_LN_XCHG = OFF_O;
 
 
 __device__ __forceinline__ float ex2(float x) {
@@ -176,6 +180,30 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): half the issue slots of the scalar forms, same rounding per lane.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
+__device__ __forceinline__ uint32_t pack_bf16_pair(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
 }
 __device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
   lo = __uint_as_float(w << 16);
@@ -426,11 +454,15 @@ __device__ __forceinline__ void softmax_store(uint32_t tmem, int q, int part, co
 
 // O accumulator (128 x 32) of (head g, tile t) -> / l -> bf16 -> O image columns g*32 .. g*32+31, split over the warpgroups
 constexpr int kOCols = 32 / kParts;
+__device__ __forceinline__ void epi_o_store(uint32_t sb, int g, int t, float inv_l, int q, int part, int lane, const uint32_t (&a)[kOCols]);
 __device__ __forceinline__ void epi_o(uint32_t tmem, uint32_t sb, int g, int t, int obuf, float inv_l, int q, int part, int lane) {
-  const int r = t * 128 + q * 32 + lane;
   uint32_t a[kOCols];
   tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_O + obuf * 32 + part * kOCols, a);
   tmem_wait_ld();
+  epi_o_store(sb, g, t, inv_l, q, part, lane, a);
+}
+__device__ __forceinline__ void epi_o_store(uint32_t sb, int g, int t, float inv_l, int q, int part, int lane, const uint32_t (&a)[kOCols]) {
+  const int r = t * 128 + q * 32 + lane;
   const uint32_t row = sb + OFF_O + (g >> 1) * kXChunkBytes + r * 128;
 #pragma unroll
   for (int i = 0; i < kOCols / 8; ++i) {
@@ -582,30 +614,34 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec,
   const int c0 = part * kLnCols;                         // first column of this thread
   const uint32_t xrow = sb + OFF_X + (c0 >> 6) * kXChunkBytes + r * 128;
   const int u0 = (c0 & 63) >> 3;
-  float v[kLnCols];
+  f32x2 v[kLnCols / 2];
   uint32_t acc[kLnCols];
   tmem_ld_cols(taddr, acc);
   tmem_wait_ld();
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  f32x2 s2 = pack2(0.f, 0.f), q2 = pack2(0.f, 0.f);
 #pragma unroll
   for (int u = 0; u < kLnUnits; ++u) {   // 16-byte unit = 8 columns
     const uint4 xr = ld_shared_v4(xrow + (((u0 + u) ^ (r & 7)) << 4));
-    float x[8];
-    unpack_bf16x2(xr.x, x[0], x[1]); unpack_bf16x2(xr.y, x[2], x[3]);
-    unpack_bf16x2(xr.z, x[4], x[5]); unpack_bf16x2(xr.w, x[6], x[7]);
-    const float4 b0 = lds_f4(bias + u * 32), b1 = lds_f4(bias + u * 32 + 16);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const uint4 b0 = ld_shared_v4(bias + u * 32), b1 = ld_shared_v4(bias + u * 32 + 16);
+    const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+    const f32x2 bb[4] = {pack2(__uint_as_float(b0.x), __uint_as_float(b0.y)), pack2(__uint_as_float(b0.z), __uint_as_float(b0.w)),
+                         pack2(__uint_as_float(b1.x), __uint_as_float(b1.y)), pack2(__uint_as_float(b1.z), __uint_as_float(b1.w))};
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      const float y0 = __uint_as_float(acc[u * 8 + j]) + bb[j] + x[j];
-      const float y1 = __uint_as_float(acc[u * 8 + j + 1]) + bb[j + 1] + x[j + 1];
-      v[u * 8 + j] = y0; v[u * 8 + j + 1] = y1;
-      s0 += y0; s1 += y1;
-      q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
+    for (int j = 0; j < 4; ++j) {
+      const f32x2 a2 = pack2(__uint_as_float(acc[u * 8 + 2 * j]), __uint_as_float(acc[u * 8 + 2 * j + 1]));
+      const f32x2 y = add2(add2(a2, bb[j]), bf16x2_to_f32x2(xw[j]));
+      v[u * 4 + j] = y;
+      s2 = add2(s2, y);
+      q2 = fma2(y, y, q2);
     }
   }
-  st_shared_f32(xchg + (part * 128 + rt) * 4, s0 + s1);
-  st_shared_f32(xchg + kXchgArray + (part * 128 + rt) * 4, q0 + q1);
+  {
+    float sa, sb2, qa, qb;
+    unpack2(s2, sa, sb2);
+    unpack2(q2, qa, qb);
+    st_shared_f32(xchg + (part * 128 + rt) * 4, sa + sb2);
+    st_shared_f32(xchg + kXchgArray + (part * 128 + rt) * 4, qa + qb);
+  }
   named_bar_sync(1 + q, 32 * kParts);
   float sum = 0.f, sq = 0.f;
 #pragma unroll
@@ -617,28 +653,34 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec,
   const float var = fmaxf(fmaf(-mean, mean, sq * (1.0f / 128.0f)), 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float shift = -mean * rstd;
+  const f32x2 rstd2 = pack2(rstd, rstd), shift2 = pack2(shift, shift);
 #pragma unroll
   for (int u = 0; u < kLnUnits; ++u) {
-    const float4 g0 = lds_f4(gam + u * 32), g1 = lds_f4(gam + u * 32 + 16);
-    const float4 e0 = lds_f4(bet + u * 32), e1 = lds_f4(bet + u * 32 + 16);
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-    float o[8];
+    const uint4 g0 = ld_shared_v4(gam + u * 32), g1 = ld_shared_v4(gam + u * 32 + 16);
+    const uint4 e0 = ld_shared_v4(bet + u * 32), e1 = ld_shared_v4(bet + u * 32 + 16);
+    const f32x2 gg[4] = {pack2(__uint_as_float(g0.x), __uint_as_float(g0.y)), pack2(__uint_as_float(g0.z), __uint_as_float(g0.w)),
+                         pack2(__uint_as_float(g1.x), __uint_as_float(g1.y)), pack2(__uint_as_float(g1.z), __uint_as_float(g1.w))};
+    const f32x2 ee[4] = {pack2(__uint_as_float(e0.x), __uint_as_float(e0.y)), pack2(__uint_as_float(e0.z), __uint_as_float(e0.w)),
+                         pack2(__uint_as_float(e1.x), __uint_as_float(e1.y)), pack2(__uint_as_float(e1.z), __uint_as_float(e1.w))};
+    f32x2 o[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[u * 8 + j], rstd, shift), gg[j], ee[j]);
+    for (int j = 0; j < 4; ++j) o[j] = fma2(fma2(v[u * 4 + j], rstd2, shift2), gg[j], ee[j]);
     // padding rows 280..287 stay zero: their accumulators are fed by padding rows of the O image (exchange scratch of
     // the tail tile) and must not leak non-finite values into the V image of the next layer
-    if (r < kS)
-      st_shared_v4(xrow + (((u0 + u) ^ (r & 7)) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                   pack_bf16x2(o[6], o[7]));
-    if (h_out_seq != nullptr && r < kS) {
-      float4* dst = reinterpret_cast<float4*>(h_out_seq + r * kD + c0 + u * 8);
-      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    if (r < kS) {
+      st_shared_v4(xrow + (((u0 + u) ^ (r & 7)) << 4), pack_bf16_pair(o[0]), pack_bf16_pair(o[1]), pack_bf16_pair(o[2]), pack_bf16_pair(o[3]));
+      if (h_out_seq != nullptr) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) unpack2(o[j], f[2 * j], f[2 * j + 1]);
+        float4* dst = reinterpret_cast<float4*>(h_out_seq + r * kD + c0 + u * 8);
+        dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+        dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
     }
   }
-  // the exchange slots are reused by the next tile: make sure every reader is done before anyone overwrites them
-  named_bar_sync(1 + q, 32 * kParts);
+  // No trailing barrier: consecutive tiles alternate between two exchange areas (see the call sites), and a warp can only
+  // reach tile t + 2 after every warp of its quadrant has passed the barrier of tile t + 1, i.e. finished reading tile t.
 }
 
 // FFN1 accumulators (chunk c = 64 hidden units, tile t), split over the warpgroups: load + bias
@@ -973,8 +1015,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               named_bar_sync(1 + q, 32 * kParts);                          // exchange the partial row maxima
 #pragma unroll
               for (int pp = 0; pp < kParts; ++pp) m = fmaxf(m, ld_shared_f32(xmax_row + pp * 512));
-              // P.V(t-1) was issued a score load ago: it has all but always consumed P by now
-              if (t > 0) { mbar_wait(misc + MB_PV_DONE, (n_head + t - 1) & 1); tc_fence_after_sync(); }
+              // P.V(t-1) was issued a score load ago: it has all but always consumed P by now.  Its O accumulator is
+              // fetched here and written out after the exponentials (the TMEM round trip hides under them).
+              uint32_t oa[kOCols];
+              if (t > 0) {
+                mbar_wait(misc + MB_PV_DONE, (n_head + t - 1) & 1);
+                tc_fence_after_sync();
+                tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_O + ((n_head + t - 1) & 1) * 32 + part * kOCols, oa);
+              }
               tl_event(p, tl, 260 + t, tl_n);   // PV_DONE(t-1) seen
               const float sum = softmax_exp_store(tmem, q, part, v, m);
               tl_event(p, tl, 250 + t, tl_n);   // exponentials done, P stored
@@ -982,6 +1030,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               tc_fence_before_sync();
               warp_arrive(misc + MB_P_READY, lane);
               tl_event(p, tl, 270 + t, tl_n);   // P(t) stored
+              if (t > 0) {
+                tmem_wait_ld();
+                epi_o_store(sb, g, t - 1, inv_prev, q, part, lane, oa);
+              }
             } else if (t == 2) {
               mbar_wait(misc + MB_S_DONE, (n_head + 2) & 1);
               tc_fence_after_sync();
@@ -999,8 +1051,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               tc_fence_after_sync();
             }
             if (t > 0) {
-              if (t < 3) epi_o(tmem, sb, g, t - 1, (n_head + t - 1) & 1, inv_prev, q, part, lane);
-              else if (q == 0) epi_o_tail(tmem, sb, g, (n_head + 2) & 1, part, lane);
+              if (t == 2) epi_o(tmem, sb, g, 1, (n_head + 1) & 1, inv_prev, q, part, lane);
+              else if (t == 3 && q == 0) epi_o_tail(tmem, sb, g, (n_head + 2) & 1, part, lane);
               tc_fence_before_sync();
               fence_proxy_async_smem();
               warp_arrive(misc + MB_O_FREE + 8 * ((n_head + t - 1) & 1), lane);
@@ -1080,7 +1132,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         tl_event(p, tl, 281, tl_n);   // OUT_DONE seen
 #pragma unroll 1
         for (int t = 0; t < 3; ++t)
-          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 1, t, q, part, lane, miscb + MISC_XMAX, nullptr);
+          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 1, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, nullptr);
         tc_fence_before_sync();
         fence_proxy_async_smem();
         warp_arrive(misc + MB_X1_READY, lane);
@@ -1120,7 +1172,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         float* ho = (l == L - 1) ? p.h_out + seq * (int64_t)kS * kD : nullptr;
 #pragma unroll 1
         for (int t = 0; t < 3; ++t)
-          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 2, t, q, part, lane, miscb + MISC_XMAX, ho);
+          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, ho);
         tc_fence_before_sync();
         fence_proxy_async_smem();
         if (l == L - 1) warp_arrive(misc + MB_X_FREE, lane);

@@ -102,10 +102,10 @@ enum : uint32_t {
   MB_O_FREE = 136,     // 2 x warp : O accumulator buffer b read out, O image columns written
   MB_OUT_DONE = 152,   // commit: out_proj accumulators complete
   MB_X1_READY = 160,   // warp  : LayerNorm1 written to X
-  MB_F1_DONE = 168,    // 2 x commit: FFN1 accumulator buffer b complete
-  MB_F1_FREE = 184,    // 2 x warp  : FFN1 accumulator buffer b read out
-  MB_HID_READY = 200,  // warp  : hidden chunk image complete (all three row tiles)
-  MB_F2_DONE = 208,    // 2 x commit: FFN2 partial product over hidden buffer b complete (buffer free / final result)
+  MB_F1_DONE = 168,    // commit: FFN1 accumulator tile (128 rows x 128 hidden units) complete
+  MB_F1_FREE = 176,    // warp  : FFN1 accumulator tile read out
+  MB_F2_DONE = 184,    // 3 x commit: FFN2 partial product of row tile t complete (hidden rows of the tile free / final result)
+  MB_HID_READY = 208,  // warp  : hidden image rows of one row tile (two 64-unit chunks) complete
   MB_X2_READY = 224,   // warp  : LayerNorm2 written to X
   MB_VEC_FULL = 232,   // commit: per-layer vector block landed in shared memory
   MB_BIAS_FULL = 240,  // 2 x commit: in_proj bias of head g landed in buffer g & 1
@@ -683,12 +683,12 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec,
   // reach tile t + 2 after every warp of its quadrant has passed the barrier of tile t + 1, i.e. finished reading tile t.
 }
 
-// FFN1 accumulators (chunk c = 64 hidden units, tile t), split over the warpgroups: load + bias
-constexpr int kActCols = 64 / kParts;
-__device__ __forceinline__ void act_load(uint32_t tmem, uint32_t vec, int c, int buf, int q, int part, float (&f)[kActCols]) {
-  const uint32_t bias = vec + 4 * (kVecBL1 + c * 64 + part * kActCols);
+// FFN1 accumulators (pair pr = hidden units 128 pr .. 128 pr + 127, one row tile), split over the warpgroups: load + bias
+constexpr int kActCols = 128 / kParts;
+__device__ __forceinline__ void act_load(uint32_t tmem, uint32_t vec, int pr, int q, int part, float (&f)[kActCols]) {
+  const uint32_t bias = vec + 4 * (kVecBL1 + pr * 128 + part * kActCols);
   uint32_t a[kActCols];
-  tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_F1 + buf * 64 + part * kActCols, a);
+  tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_F1 + part * kActCols, a);
   tmem_wait_ld();
 #pragma unroll
   for (int u = 0; u < kActCols / 4; ++u) {
@@ -697,8 +697,9 @@ __device__ __forceinline__ void act_load(uint32_t tmem, uint32_t vec, int c, int
     f[u * 4 + 2] = __uint_as_float(a[u * 4 + 2]) + b.z; f[u * 4 + 3] = __uint_as_float(a[u * 4 + 3]) + b.w;
   }
 }
-// GELU / ReLU -> bf16 -> hidden chunk image (K-chunk c of FFN2's A operand)
-__device__ __forceinline__ void act_store(uint32_t sb, int c, int t, int act, int q, int part, int lane, float (&f)[kActCols]) {
+// GELU / ReLU -> bf16 -> hidden images (K-chunks of FFN2's A operand): the pair's first 64 units go to buffer 0, the
+// others to buffer 1.  Padding rows 280..287 are not written (the O region's padding rows hold scratch data).
+__device__ __forceinline__ void act_store(uint32_t sb, int t, int act, int q, int part, int lane, float (&f)[kActCols]) {
   const int r = t * 128 + q * 32 + lane;
   if (act == AFT_ACT_GELU) {
 #pragma unroll
@@ -707,11 +708,15 @@ __device__ __forceinline__ void act_store(uint32_t sb, int c, int t, int act, in
 #pragma unroll
     for (int j = 0; j < kActCols; ++j) f[j] = fmaxf(f[j], 0.f);
   }
-  const uint32_t row = sb + OFF_O + (c & 1) * kHidBytes + r * 128;
+  const int c0 = part * kActCols;                       // first column inside the 128-wide pair
+  const uint32_t row = sb + OFF_O + (c0 >> 6) * kHidBytes + r * 128;
+  const int u0 = (c0 & 63) >> 3;
+  if (r < kS) {
 #pragma unroll
-  for (int u = 0; u < kActCols / 8; ++u)
-    st_shared_v4(row + (((part * (kActCols / 8) + u) ^ (r & 7)) << 4), pack_bf16x2(f[8 * u], f[8 * u + 1]),
-                 pack_bf16x2(f[8 * u + 2], f[8 * u + 3]), pack_bf16x2(f[8 * u + 4], f[8 * u + 5]), pack_bf16x2(f[8 * u + 6], f[8 * u + 7]));
+    for (int u = 0; u < kActCols / 8; ++u)
+      st_shared_v4(row + (((u0 + u) ^ (r & 7)) << 4), pack_bf16x2(f[8 * u], f[8 * u + 1]),
+                   pack_bf16x2(f[8 * u + 2], f[8 * u + 3]), pack_bf16x2(f[8 * u + 4], f[8 * u + 5]), pack_bf16x2(f[8 * u + 6], f[8 * u + 7]));
+  }
 }
 
 // =============================================================================================
@@ -764,9 +769,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
   if (threadIdx.x == 0) {
     const uint32_t commit_bars[] = {MB_VEC_FULL, MB_BIAS_FULL, MB_BIAS_FULL + 8, MB_X_FULL, MB_ATTN_DONE, MB_W_FULL, MB_W_FULL + 8, MB_W_FULL + 16, MB_W_FULL + 24,
                                     MB_W_EMPTY, MB_W_EMPTY + 8, MB_W_EMPTY + 16, MB_W_EMPTY + 24, MB_QKV_DONE, MB_S_DONE,
-                                    MB_PV_DONE, MB_OUT_DONE, MB_F1_DONE, MB_F1_DONE + 8, MB_F2_DONE, MB_F2_DONE + 8};
+                                    MB_PV_DONE, MB_OUT_DONE, MB_F1_DONE, MB_F2_DONE, MB_F2_DONE + 8, MB_F2_DONE + 16};
     const uint32_t warp_bars[] = {MB_X_FREE, MB_QKV_READY, MB_S_LOADED, MB_P_READY, MB_O_FREE, MB_O_FREE + 8, MB_X1_READY,
-                                  MB_F1_FREE, MB_F1_FREE + 8, MB_HID_READY, MB_X2_READY};
+                                  MB_F1_FREE, MB_HID_READY, MB_X2_READY};
     for (uint32_t b : commit_bars) mbar_init(misc + b, 1);
     for (uint32_t b : warp_bars) mbar_init(misc + b, kComputeWarps);
     fence_mbar_init();
@@ -792,10 +797,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         bulk_g2s(sb + OFF_X, p.x_images + seq * (int64_t)kXImageBytes, kXImageBytes, misc + MB_X_FULL);
         for (int l = 0; l < L; ++l) {
           const TcLayer& W = p.layers[l];
-          for (int g = 0; g < 4; ++g, ++n_in) {
+          // the in_proj slot: four head slices per layer, then (FFN) the second K-chunk of each W1 pair
+          auto fill_w = [&](const char* src, uint32_t bytes) {
             if (n_in > 0) mbar_wait_relaxed(misc + MB_W_EMPTY, (n_in - 1) & 1);
-            mbar_arrive_expect_tx(misc + MB_W_FULL, kWInSlice);
-            bulk_g2s(sb + OFF_W, reinterpret_cast<const char*>(W.w_in) + g * kWInSlice, kWInSlice, misc + MB_W_FULL);
+            mbar_arrive_expect_tx(misc + MB_W_FULL, bytes);
+            bulk_g2s(sb + OFF_W, src, bytes, misc + MB_W_FULL);
+            ++n_in;
+          };
+          auto fill_ring = [&](const char* src) {
+            const int slot = n_ring % 3;
+            const uint32_t fill = n_ring / 3;
+            if (fill > 0) mbar_wait_relaxed(misc + MB_W_EMPTY + 8 * (1 + slot), (fill - 1) & 1);
+            mbar_arrive_expect_tx(misc + MB_W_FULL + 8 * (1 + slot), kRingSlot);
+            bulk_g2s(sb + OFF_QKV + slot * kRingSlot, src, kRingSlot, misc + MB_W_FULL + 8 * (1 + slot));
+            ++n_ring;
+          };
+          for (int g = 0; g < 4; ++g) {
+            fill_w(reinterpret_cast<const char*>(W.w_in) + g * kWInSlice, kWInSlice);
             // bias buffer g & 1 was last read by the epilogue of head g-2, which finished before QKV(g-1) was even issued
             mbar_arrive_expect_tx(misc + MB_BIAS_FULL + 8 * (g & 1), kQkvBiasBytes);
             bulk_g2s(miscb + MISC_QKV_BIAS + (g & 1) * kQkvBiasBytes, W.b_in + g * 96, kQkvBiasBytes, misc + MB_BIAS_FULL + 8 * (g & 1));
@@ -804,16 +822,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           ++n_attn;
           mbar_arrive_expect_tx(misc + MB_VEC_FULL, kVecBlockBytes);
           bulk_g2s(sb + OFF_VEC, W.b_in + kVecBlock, kVecBlockBytes, misc + MB_VEC_FULL);
-          for (int i = 0; i < 10; ++i, ++n_ring) {   // ring order: Wout0 Wout1 | W1c0 W2c0 | W1c1 W2c1 | ...
-            const int slot = n_ring % 3;
-            const uint32_t fill = n_ring / 3;
-            if (fill > 0) mbar_wait_relaxed(misc + MB_W_EMPTY + 8 * (1 + slot), (fill - 1) & 1);
-            const char* src = i < 2 ? reinterpret_cast<const char*>(W.w_out) + i * kRingSlot
-                                    : ((i & 1) == 0 ? reinterpret_cast<const char*>(W.w_l1) + ((i - 2) >> 1) * kRingSlot
-                                                    : reinterpret_cast<const char*>(W.w_l2) + ((i - 3) >> 1) * kRingSlot);
-            mbar_arrive_expect_tx(misc + MB_W_FULL + 8 * (1 + slot), kRingSlot);
-            bulk_g2s(sb + OFF_QKV + slot * kRingSlot, src, kRingSlot, misc + MB_W_FULL + 8 * (1 + slot));
-          }
+          // ring order: Wout k0, Wout k1 | W1 pair 0 k0 | W2 c0, W2 c1 | W1 pair 1 k0 | W2 c2, W2 c3; the k1 halves of
+          // the W1 pairs go to the (idle) in_proj slot, so that a whole pair plus the W2 chunks in use are resident together
+          const char* wout = reinterpret_cast<const char*>(W.w_out);
+          const char* wl1 = reinterpret_cast<const char*>(W.w_l1);
+          const char* wl2 = reinterpret_cast<const char*>(W.w_l2);
+          fill_ring(wout);
+          fill_ring(wout + kRingSlot);
+          fill_ring(wl1);
+          fill_w(wl1 + kRingSlot, kRingSlot);
+          fill_ring(wl2);
+          fill_ring(wl2 + kRingSlot);
+          fill_ring(wl1 + 2 * kRingSlot);
+          fill_w(wl1 + 3 * kRingSlot, kRingSlot);
+          fill_ring(wl2 + 2 * kRingSlot);
+          fill_ring(wl2 + 3 * kRingSlot);
         }
       }
     } else if (warp == kMmaWarp) {
@@ -833,7 +856,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
 
       for (int64_t seq = blockIdx.x; seq < p.nseq; seq += gridDim.x) {
         x_full.wait(misc + MB_X_FULL);
-        for (int l = 0; l < L; ++l, ++n_layers_done, ring_base += 10) {
+        for (int l = 0; l < L; ++l, ++n_layers_done, ring_base += 8) {
           const bool tl = AFT_TL_ON(p.timeline != nullptr && blockIdx.x == 0 && seq == (int64_t)gridDim.x && l == 1 && lane == 0);
           // X and the accumulator columns [0,384) are free once the previous LayerNorm2 has finished
           if (n_layers_done > 0) x2_ready.wait(misc + MB_X2_READY);
@@ -915,50 +938,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             mma_commit(misc + MB_OUT_DONE, el);
             tl_event(p, tl, 161, tl_n);   // out_proj issued
           }
-          // ---- FFN: FFN1 tiles double buffered in TMEM; FFN2 partial products accumulate over the 4 hidden chunks
+          // ---- FFN.  FFN1 runs as N = 128 MMAs over pairs of hidden chunks (tile k = 3 pr + t, single accumulator tile in
+          // TMEM); the FFN2 partial products of row tile t are issued as soon as the GELU of that tile is stored, right
+          // behind the next FFN1 tile.  W1 pair: K-chunk 0 in a ring slot, K-chunk 1 in the in_proj slot.
           x1_ready.wait(misc + MB_X1_READY);
           tc_fence_after_sync();
           tl_event(p, tl, 170, tl_n);   // X1_READY seen
-          for (int c = 0; c < 4; ++c) {
-            uint32_t w1c = 0;
-            for (int t = 0; t < 3; ++t, ++n_f1) {
-              const int buf = n_f1 & 1;
-              if (n_f1 >= 2) mbar_wait(misc + MB_F1_FREE + 8 * buf, ((n_f1 >> 1) - 1) & 1);
-              tc_fence_after_sync();
-              tl_event(p, tl, 196, tl_n);   // F1_FREE seen
-              if (t == 0) w1c = ring_wait(ring_base + 2 + 2 * c);          // linear1 rows 64c .. 64c+63 (K = 128)
-              tl_event(p, tl, 197, tl_n);   // W1 chunk resident
-              issue_gemm_sw128(tmem, TM_F1 + buf * 64, sb + OFF_X + t * 128 * 128, kXChunkBytes, w1c, 64 * 128, 8, kIdescN64, false, el);
-              mma_commit(misc + MB_F1_DONE + 8 * buf, el);
-              tl_event(p, tl, 180 + 3 * c + t, tl_n);   // FFN1(c,t) issued
-              if (t == 2) ring_release(ring_base + 2 + 2 * c);
-              if (t == 1 && c > 0) {
-                // FFN2 partial of the previous chunk, after both FFN1 buffers have been refilled: the GELU warps find
-                // the next accumulator tile ready instead of waiting behind these twelve MMAs
-                tl_event(p, tl, 192, tl_n);   // waiting HID_READY
-                hid_ready.wait(misc + MB_HID_READY);
-                tc_fence_after_sync();
-                tl_event(p, tl, 193, tl_n);   // HID_READY seen
-                const uint32_t w2 = ring_wait(ring_base + 3 + 2 * (c - 1));
-                tl_event(p, tl, 194, tl_n);   // W2 chunk resident
-                for (int tt = 0; tt < 3; ++tt)
-                  issue_gemm_sw128(tmem, TM_OUT + tt * 128, sb + OFF_O + ((c - 1) & 1) * kHidBytes + tt * 128 * 128, 0, w2, 0, 4,
-                                   kIdescN128, c - 1 > 0, el);
-                ring_release(ring_base + 3 + 2 * (c - 1));
-                mma_commit(misc + MB_F2_DONE + 8 * ((c - 1) & 1), el);
-                tl_event(p, tl, 195, tl_n);   // FFN2(c-1) issued
-              }
-            }
-          }
-          hid_ready.wait(misc + MB_HID_READY);
-          tc_fence_after_sync();
           {
-            const uint32_t w2 = ring_wait(ring_base + 9);
-            for (int tt = 0; tt < 3; ++tt)
-              issue_gemm_sw128(tmem, TM_OUT + tt * 128, sb + OFF_O + kHidBytes + tt * 128 * 128, 0, w2, 0, 4, kIdescN128, true, el);
-            ring_release(ring_base + 9);
-            mma_commit(misc + MB_F2_DONE + 8, el);
-            tl_event(p, tl, 199, tl_n);   // FFN2(3) issued
+            constexpr uint32_t kHi = (uint32_t)(desc_k_sw128_const() >> 32);
+            auto desc128 = [&](uint32_t saddr) -> uint32_t { return (uint32_t)desc_k_sw128_const() | ((saddr >> 4) & 0x3FFF); };
+            auto issue_f2 = [&](int j) {   // FFN2 partial products of tile j % 3 over the two hidden chunks of pair j / 3
+              const int pj = j / 3, tj = j - 3 * pj;
+              hid_ready.wait(misc + MB_HID_READY);
+              tc_fence_after_sync();
+              const uint32_t w2a = ring_wait(ring_base + 3 + 3 * pj), w2b = ring_wait(ring_base + 4 + 3 * pj);
+              const uint32_t d = tmem + TM_OUT + tj * 128;
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const uint32_t a_lo = desc128(sb + OFF_O + cc * kHidBytes + tj * 128 * 128), b_lo = desc128(cc == 0 ? w2a : w2b);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  mma_ss(d, ((uint64_t)kHi << 32) | (a_lo + ks * 2), ((uint64_t)kHi << 32) | (b_lo + ks * 2), kIdescN128,
+                         pj > 0 || cc > 0 || ks > 0, el);
+              }
+              mma_commit(misc + MB_F2_DONE + 8 * tj, el);
+              if (tj == 2) { ring_release(ring_base + 3 + 3 * pj); ring_release(ring_base + 4 + 3 * pj); }
+              tl_event(p, tl, 190 + j, tl_n);   // FFN2(j) issued
+            };
+            uint32_t w1a = 0, w1b = 0;
+            for (int k = 0; k < 6; ++k, ++n_f1) {
+              const int pr = k / 3, t = k - 3 * pr;
+              if (t == 0) {
+                w1a = ring_wait(ring_base + 2 + 3 * pr);
+                mbar_wait(misc + MB_W_FULL, n_in & 1);
+                tc_fence_after_sync();
+                w1b = sb + OFF_W;
+              }
+              if (n_f1 >= 1) mbar_wait(misc + MB_F1_FREE, (n_f1 - 1) & 1);
+              tc_fence_after_sync();
+              {
+                const uint32_t a0 = desc128(sb + OFF_X + t * 128 * 128), a1 = desc128(sb + OFF_X + kXChunkBytes + t * 128 * 128);
+                const uint32_t b0 = desc128(w1a), b1 = desc128(w1b);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                  mma_ss(tmem + TM_F1, ((uint64_t)kHi << 32) | ((ks < 4 ? a0 : a1) + (ks & 3) * 2),
+                         ((uint64_t)kHi << 32) | ((ks < 4 ? b0 : b1) + (ks & 3) * 2), kIdescN128, ks > 0, el);
+              }
+              mma_commit(misc + MB_F1_DONE, el);
+              tl_event(p, tl, 180 + k, tl_n);   // FFN1(k) issued
+              if (t == 2) {   // the pair's weights are free once these MMAs have completed
+                ring_release(ring_base + 2 + 3 * pr);
+                mma_commit(misc + MB_W_EMPTY, el);
+                ++n_in;
+              }
+              if (k >= 1) issue_f2(k - 1);
+            }
+            issue_f2(5);
           }
         }
       }
@@ -1137,36 +1172,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         fence_proxy_async_smem();
         warp_arrive(misc + MB_X1_READY, lane);
         tl_event(p, tl, 282, tl_n);   // LayerNorm1 done
-        // ---- FFN1 epilogues: bias + GELU -> hidden chunk images
+        // ---- FFN1 epilogues: bias + GELU -> hidden images.  Tile k = 3 pr + t of this layer: F1_DONE / F1_FREE / HID_READY
+        // complete six times per layer (phase parity k & 1), F2_DONE[t] twice (pair 0: rows free again, pair 1: final).
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (c >= 2) mbar_wait(misc + MB_F2_DONE + 8 * (c & 1), 0);   // FFN2(c-2) has consumed hidden buffer c & 1
-#pragma unroll 1
-          for (int t = 0; t < 3; ++t) {
-            // FFN1 tile #k of this CTA has k = 12 * n_layer + 3c + t: buffer k & 1, phase (k >> 1) & 1 (12 * n_layer drops out)
-            const int k = 3 * c + t, buf = k & 1;
-            const bool active = t < 2 || tile2_active;
-            mbar_wait(misc + MB_F1_DONE + 8 * buf, (k >> 1) & 1);
-            tc_fence_after_sync();
-            tl_event(p, tl, 300 + 3 * c + t, tl_n);   // F1_DONE(c,t) seen
-            if (active) {   // accumulators defined and consumed inside one branch (see the softmax tiles)
-              float f[kActCols];
-              act_load(tmem, vec, c, buf, q, part, f);
-              tc_fence_before_sync();
-              warp_arrive(misc + MB_F1_FREE + 8 * buf, lane);
-              act_store(sb, c, t, p.activation, q, part, lane, f);
-            } else {
-              tc_fence_before_sync();
-              warp_arrive(misc + MB_F1_FREE + 8 * buf, lane);
-            }
-            tl_event(p, tl, 320 + 3 * c + t, tl_n);   // GELU(c,t) stored
+        for (int k = 0; k < 6; ++k) {
+          const int pr = k >= 3 ? 1 : 0, t = k - 3 * pr;
+          const bool active = t < 2 || tile2_active;
+          mbar_wait(misc + MB_F1_DONE, k & 1);
+          tc_fence_after_sync();
+          tl_event(p, tl, 300 + k, tl_n);   // F1_DONE(k) seen
+          if (active) {   // accumulators defined and consumed inside one branch (see the softmax tiles)
+            float f[kActCols];
+            act_load(tmem, vec, pr, q, part, f);
+            tc_fence_before_sync();
+            warp_arrive(misc + MB_F1_FREE, lane);
+            // the hidden rows of this tile still feed the FFN2 partial products of pair 0
+            if (pr == 1) mbar_wait(misc + MB_F2_DONE + 8 * t, 0);
+            act_store(sb, t, p.activation, q, part, lane, f);
+          } else {
+            tc_fence_before_sync();
+            warp_arrive(misc + MB_F1_FREE, lane);
           }
+          tl_event(p, tl, 320 + k, tl_n);   // GELU(k) stored
           fence_proxy_async_smem();
           warp_arrive(misc + MB_HID_READY, lane);
         }
         // ---- linear2 epilogue: + bias + residual -> LayerNorm2 -> X (+ fp32 result after the last layer)
-        mbar_wait(misc + MB_F2_DONE, 1);        // FFN2(2) and FFN2(3): second completion of each barrier in this layer
-        mbar_wait(misc + MB_F2_DONE + 8, 1);
+        mbar_wait(misc + MB_F2_DONE, 1);        // second completion of each tile's barrier in this layer (in issue order:
+        mbar_wait(misc + MB_F2_DONE + 8, 1);    // the last one covers them all, the others return at once)
+        mbar_wait(misc + MB_F2_DONE + 16, 1);
         tc_fence_after_sync();
         tl_event(p, tl, 340, tl_n);   // FFN2 complete seen
         float* ho = (l == L - 1) ? p.h_out + seq * (int64_t)kS * kD : nullptr;
@@ -1306,7 +1340,7 @@ bool tc_weights_pack(TcWeights& w, const std::vector<LayerPackF32>& src, const C
     // out_proj: one image, 128 rows, K = 128 (2 chunks)
     pack_image_kernel<<<(128 * 2 * 8 + 255) / 256, 256, 0, st>>>(S.out_w, kD, bf(T.w_out), 1, 128, 2, 0, 0, 0, 0, 0, 1.f);
     // linear1: 4 images of 64 rows, K = 128
-    pack_image_kernel<<<(4 * 64 * 2 * 8 + 255) / 256, 256, 0, st>>>(S.l1_w, kD, bf(T.w_l1), 4, 64, 2, 0, 64, 0, 0, 0, 1.f);
+    pack_image_kernel<<<(2 * 128 * 2 * 8 + 255) / 256, 256, 0, st>>>(S.l1_w, kD, bf(T.w_l1), 2, 128, 2, 0, 128, 0, 0, 0, 1.f);
     // linear2: 4 images of 128 rows, one K-chunk each (columns 64c .. 64c+63 of the [128, 256] matrix)
     pack_image_kernel<<<(4 * 128 * 1 * 8 + 255) / 256, 256, 0, st>>>(S.l2_w, kFF, bf(T.w_l2), 4, 128, 1, 0, 0, 0, 64, 0, 1.f);
     pack_vec_kernel<<<(kVecPerLayer + 255) / 256, 256, 0, st>>>(S, const_cast<float*>(T.b_in), qscale);

@@ -105,7 +105,9 @@ enum : uint32_t {
   MB_F1_DONE = 168,    // commit: FFN1 accumulator tile (128 rows x 128 hidden units) complete
   MB_F1_FREE = 176,    // warp  : FFN1 accumulator tile read out
   MB_F2_DONE = 184,    // 3 x commit: FFN2 partial product of row tile t complete (hidden rows of the tile free / final result)
-  MB_HID_READY = 208,  // warp  : hidden image rows of one row tile (two 64-unit chunks) complete
+  MB_HID_READY = 208,  // 2 x warp : hidden image rows of FFN tile k (two 64-unit chunks) complete, barrier k & 1.  Two barriers:
+                       // FFN1(k+1) is issued before the issuer waits for tile k, so a single barrier could collect a fast
+                       // warp's arrival for tile k+1 while a slow warp still owes the one for tile k
   MB_X2_READY = 224,   // warp  : LayerNorm2 written to X
   MB_VEC_FULL = 232,   // commit: per-layer vector block landed in shared memory
   MB_BIAS_FULL = 240,  // 2 x commit: in_proj bias of head g landed in buffer g & 1
@@ -771,7 +773,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
                                     MB_W_EMPTY, MB_W_EMPTY + 8, MB_W_EMPTY + 16, MB_W_EMPTY + 24, MB_QKV_DONE, MB_S_DONE,
                                     MB_PV_DONE, MB_OUT_DONE, MB_F1_DONE, MB_F2_DONE, MB_F2_DONE + 8, MB_F2_DONE + 16};
     const uint32_t warp_bars[] = {MB_X_FREE, MB_QKV_READY, MB_S_LOADED, MB_P_READY, MB_O_FREE, MB_O_FREE + 8, MB_X1_READY,
-                                  MB_F1_FREE, MB_HID_READY, MB_X2_READY};
+                                  MB_F1_FREE, MB_HID_READY, MB_HID_READY + 8, MB_X2_READY};
     for (uint32_t b : commit_bars) mbar_init(misc + b, 1);
     for (uint32_t b : warp_bars) mbar_init(misc + b, kComputeWarps);
     fence_mbar_init();
@@ -844,7 +846,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
       // The whole warp runs the schedule converged (all lanes poll the barriers, addresses stay warp-uniform and live in
       // uniform registers); only the tcgen05.mma / tcgen05.commit instructions are predicated on the elected lane.
       const bool el = elect_one();
-      Phase x_full, x2_ready, qkv_ready, s_loaded, p_ready, x1_ready, hid_ready;
+      Phase x_full, x2_ready, qkv_ready, s_loaded, p_ready, x1_ready, hid_ready[2];
       uint32_t n_in = 0, ring_base = 0, n_pv = 0, n_f1 = 0, n_layers_done = 0, tl_n = 0;
       // ring entry `idx` (global index): wait until it is resident, return its address; release = commit its empty barrier
       auto ring_wait = [&](uint32_t idx) -> uint32_t {
@@ -949,7 +951,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             auto desc128 = [&](uint32_t saddr) -> uint32_t { return (uint32_t)desc_k_sw128_const() | ((saddr >> 4) & 0x3FFF); };
             auto issue_f2 = [&](int j) {   // FFN2 partial products of tile j % 3 over the two hidden chunks of pair j / 3
               const int pj = j / 3, tj = j - 3 * pj;
-              hid_ready.wait(misc + MB_HID_READY);
+              hid_ready[j & 1].wait(misc + MB_HID_READY + 8 * (j & 1));
               tc_fence_after_sync();
               const uint32_t w2a = ring_wait(ring_base + 3 + 3 * pj), w2b = ring_wait(ring_base + 4 + 3 * pj);
               const uint32_t d = tmem + TM_OUT + tj * 128;
@@ -1195,7 +1197,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           }
           tl_event(p, tl, 320 + k, tl_n);   // GELU(k) stored
           fence_proxy_async_smem();
-          warp_arrive(misc + MB_HID_READY, lane);
+          warp_arrive(misc + MB_HID_READY + 8 * (k & 1), lane);
         }
         // ---- linear2 epilogue: + bias + residual -> LayerNorm2 -> X (+ fp32 result after the last layer)
         mbar_wait(misc + MB_F2_DONE, 1);        // second completion of each tile's barrier in this layer (in issue order:

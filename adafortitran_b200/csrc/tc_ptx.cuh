@@ -63,7 +63,20 @@ __device__ __forceinline__ void mbar_wait_timeout(uint32_t bar, uint32_t parity)
         ((unsigned long long)parity << 16) | (bar & 0xFFFFu);
   __threadfence_system();
 }
+// -DAFT_TC_CHAOS: every wait is preceded by a pseudo-random, warp-uniform delay of up to ~8 us for one call in four.
+// Shakes the relative timing of the roles (MMA issuer, producer, compute warps); a protocol that relies on timing rather
+// than on its barriers then hangs into the bounded spin below and is reported by the wait-timeout diagnostics.
+__device__ __forceinline__ void chaos_delay() {
+#ifdef AFT_TC_CHAOS
+  uint32_t c;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+  c = __shfl_sync(0xFFFFFFFFu, c, 0);
+  const uint32_t h = (c ^ ((threadIdx.x >> 5) * 0x9E3779B9u) ^ (blockIdx.x * 0x85EBCA6Bu)) * 2654435761u;
+  if (((h >> 28) & 3) == 0) __nanosleep((h >> 8) & 0x1FFF);
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  chaos_delay();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     ++spins;
@@ -79,8 +92,13 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(64);
     ++spins;
+#ifdef AFT_TC_CHAOS
+    if (spins == 60000000u) mbar_wait_timeout(bar, parity);   // let the stuck compute / MMA roles report first
+    if (spins > 80000000u) __trap();
+#else
     if (spins == 2000000u) mbar_wait_timeout(bar, parity);
     if (spins > 3000000u) __trap();
+#endif
   }
 }
 

@@ -56,7 +56,7 @@ if __name__ == "__main__":
     if what == "diag":
         arm_diag()
         try:
-            forward_check("forti", 2)
+            forward_check("forti", int(os.environ.get("AFT_DIAG_BATCH", "2")))
         except Exception as e:
             print("forward failed:", str(e)[:200])
         dump_diag()

@@ -106,7 +106,7 @@ void conv_tc_dump_timeline();
 bool conv_tc_pack(const ConvPack& src, void* dst, cudaStream_t st);
 bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilots, const float* snr, const float* ds,
                         const float* dop, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st);
-bool launch_head_tc(const HeadPack& p, const void* pack, const float* h, const float* enh, float2* out, int64_t nsamples,
+bool launch_head_tc(const HeadPack& p, const void* pack, const void* himg, const float* enh, float2* out, int64_t nsamples,
                     int sm_count, cudaStream_t st);
 
 // gemm_f32.cu : C[M,N] = A[M,K] * W[N,K]^T + bias, fp32 FMA

@@ -159,7 +159,7 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const float* __restrict__ h, const float* __restrict__ enh,
+head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __restrict__ himg, const float* __restrict__ enh,
                float* __restrict__ out /* interleaved re/im */, int64_t nsamples) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
@@ -186,11 +186,13 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const float* __rest
   for (int64_t sample = blockIdx.x; sample < nsamples; sample += gridDim.x) {
     for (int part = 0; part < 2; ++part, ++n_run) {
       const int64_t seq = 2 * sample + part;
-      const float* hs = h + seq * (int64_t)kS * kD;
+      const uint8_t* hs = himg + seq * (int64_t)kXImageBytes;   // encoder output: bf16 operand image (tc_layout.cuh)
       const float* es = enh + seq * (int64_t)kPix;
       // linear_2 (encoders.py:70), Fold (patch_processors.py:69-71) and the residual (fortitran.py:228)
       for (int t = warp; t < kS; t += kThreads / 32) {
-        const float4 hv = *reinterpret_cast<const float4*>(hs + t * kD + lane * 4);
+        const uint2 hw = *reinterpret_cast<const uint2*>(hs + ximage_offset(t, (lane * 4) & ~7) + (lane & 1) * 8);
+        const float4 hv = make_float4(__uint_as_float(hw.x << 16), __uint_as_float(hw.x & 0xFFFF0000u), __uint_as_float(hw.y << 16),
+                                      __uint_as_float(hw.y & 0xFFFF0000u));
         float acc[kPatchLen];
 #pragma unroll
         for (int f = 0; f < kPatchLen; ++f) acc[f] = hv.x * w2[f].x + hv.y * w2[f].y + hv.z * w2[f].z + hv.w * w2[f].w;
@@ -276,7 +278,7 @@ bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilo
   return check_launch("frontend_tc_kernel");
 }
 
-bool launch_head_tc(const HeadPack& p, const void* pack, const float* h, const float* enh, float2* out, int64_t nsamples,
+bool launch_head_tc(const HeadPack& p, const void* pack, const void* himg, const float* enh, float2* out, int64_t nsamples,
                     int sm_count, cudaStream_t st) {
   if (cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStackSmemBytes) != cudaSuccess) {
     set_error("head_tc: cannot opt in to %d bytes of shared memory: %s", kStackSmemBytes, cudaGetErrorString(cudaGetLastError()));
@@ -284,7 +286,7 @@ bool launch_head_tc(const HeadPack& p, const void* pack, const float* h, const f
   }
   if (nsamples <= 0) return true;
   head_tc_kernel<<<(unsigned)(nsamples < sm_count ? nsamples : sm_count), kThreads, kStackSmemBytes, st>>>(
-      p, static_cast<const uint8_t*>(pack), h, enh, reinterpret_cast<float*>(out), nsamples);
+      p, static_cast<const uint8_t*>(pack), static_cast<const uint8_t*>(himg), enh, reinterpret_cast<float*>(out), nsamples);
   count_launch();
   return check_launch("head_tc_kernel");
 }

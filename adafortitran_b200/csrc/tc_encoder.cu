@@ -607,7 +607,7 @@ __device__ __forceinline__ void epi_o_tail(uint32_t tmem, uint32_t sb, int g, in
 // `vec` = shared address of the layer's vector block; `xchg` = shared address of the exchange area.
 constexpr int kLnCols = 128 / kParts, kLnUnits = kLnCols / 8;
 __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec, int which, int t, int q, int part, int lane,
-                                       uint32_t xchg, float* h_out_seq) {
+                                       uint32_t xchg, char* img_out) {
   const int rt = q * 32 + lane, r = t * 128 + rt;
   const uint32_t bias = vec + 4 * ((which == 1 ? kVecBOut : kVecBL2) + part * kLnCols);
   const uint32_t gam = vec + 4 * ((which == 1 ? kVecN1W : kVecN2W) + part * kLnCols);
@@ -670,15 +670,11 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec,
     // padding rows 280..287 stay zero: their accumulators are fed by padding rows of the O image (exchange scratch of
     // the tail tile) and must not leak non-finite values into the V image of the next layer
     if (r < kS) {
-      st_shared_v4(xrow + (((u0 + u) ^ (r & 7)) << 4), pack_bf16_pair(o[0]), pack_bf16_pair(o[1]), pack_bf16_pair(o[2]), pack_bf16_pair(o[3]));
-      if (h_out_seq != nullptr) {
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) unpack2(o[j], f[2 * j], f[2 * j + 1]);
-        float4* dst = reinterpret_cast<float4*>(h_out_seq + r * kD + c0 + u * 8);
-        dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-        dst[1] = make_float4(f[4], f[5], f[6], f[7]);
-      }
+      const uint4 pk = make_uint4(pack_bf16_pair(o[0]), pack_bf16_pair(o[1]), pack_bf16_pair(o[2]), pack_bf16_pair(o[3]));
+      const uint32_t off = r * 128 + (((u0 + u) ^ (r & 7)) << 4);
+      st_shared_v4(sb + OFF_X + (c0 >> 6) * kXChunkBytes + off, pk.x, pk.y, pk.z, pk.w);
+      // last layer: the same 16 bytes go to the sequence's image in global memory (the encoder output replaces its input)
+      if (img_out != nullptr) *reinterpret_cast<uint4*>(img_out + (c0 >> 6) * kXChunkBytes + off) = pk;
     }
   }
   // No trailing barrier: consecutive tiles alternate between two exchange areas (see the call sites), and a warp can only
@@ -725,8 +721,7 @@ __device__ __forceinline__ void act_store(uint32_t sb, int t, int act, int q, in
 // the persistent encoder kernel
 // =============================================================================================
 struct EncParams {
-  const char* x_images;       // [nseq][kXImageBytes]
-  float* h_out;               // [nseq][280][128]
+  char* x_images;             // [nseq][kXImageBytes]: residual stream images, replaced in place by the encoder output
   const TcLayer* layers;      // device table
   int num_layers;
   int activation;
@@ -846,7 +841,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
       // The whole warp runs the schedule converged (all lanes poll the barriers, addresses stay warp-uniform and live in
       // uniform registers); only the tcgen05.mma / tcgen05.commit instructions are predicated on the elected lane.
       const bool el = elect_one();
-      Phase x_full, x2_ready, qkv_ready, s_loaded, p_ready, x1_ready, hid_ready[2];
+      Phase x_full, x2_ready, qkv_ready, s_loaded, p_ready, x1_ready;
       uint32_t n_in = 0, ring_base = 0, n_pv = 0, n_f1 = 0, n_layers_done = 0, tl_n = 0;
       // ring entry `idx` (global index): wait until it is resident, return its address; release = commit its empty barrier
       auto ring_wait = [&](uint32_t idx) -> uint32_t {
@@ -951,7 +946,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             auto desc128 = [&](uint32_t saddr) -> uint32_t { return (uint32_t)desc_k_sw128_const() | ((saddr >> 4) & 0x3FFF); };
             auto issue_f2 = [&](int j) {   // FFN2 partial products of tile j % 3 over the two hidden chunks of pair j / 3
               const int pj = j / 3, tj = j - 3 * pj;
-              hid_ready[j & 1].wait(misc + MB_HID_READY + 8 * (j & 1));
+              // FFN tile J = 6 * layers_done + j of this CTA: barrier J & 1 (= j & 1), its completion number J >> 1
+              mbar_wait(misc + MB_HID_READY + 8 * (j & 1), ((6 * n_layers_done + j) >> 1) & 1);
               tc_fence_after_sync();
               const uint32_t w2a = ring_wait(ring_base + 3 + 3 * pj), w2b = ring_wait(ring_base + 4 + 3 * pj);
               const uint32_t d = tmem + TM_OUT + tj * 128;
@@ -1205,10 +1201,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         mbar_wait(misc + MB_F2_DONE + 16, 1);
         tc_fence_after_sync();
         tl_event(p, tl, 340, tl_n);   // FFN2 complete seen
-        float* ho = (l == L - 1) ? p.h_out + seq * (int64_t)kS * kD : nullptr;
+        char* img_out = (l == L - 1) ? p.x_images + seq * (int64_t)kXImageBytes : nullptr;
 #pragma unroll 1
         for (int t = 0; t < 3; ++t)
-          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, ho);
+          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, img_out);
         tc_fence_before_sync();
         fence_proxy_async_smem();
         if (l == L - 1) warp_arrive(misc + MB_X_FREE, lane);
@@ -1361,8 +1357,7 @@ size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 size_t tc_workspace_bytes(int64_t bc) {
   const size_t nseq = 2 * (size_t)bc;
-  return align_up_sz(nseq * kPix * sizeof(float), 1024) + align_up_sz(nseq * (size_t)kXImageBytes, 1024) +
-         align_up_sz(nseq * (size_t)kS * kD * sizeof(float), 1024);
+  return align_up_sz(nseq * kPix * sizeof(float), 1024) + align_up_sz(nseq * (size_t)kXImageBytes, 1024);
 }
 
 bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack& head, int activation, int sm_count,
@@ -1373,7 +1368,6 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   char* ws = static_cast<char*>(workspace);
   float* enh = reinterpret_cast<float*>(ws);
   char* ximg = ws + align_up_sz(nseq * kPix * sizeof(float), 1024);
-  float* hout = reinterpret_cast<float*>(ximg + align_up_sz(nseq * (size_t)kXImageBytes, 1024));
   mark();
   if (!launch_frontend_tc(front, w.conv_front, pilots, snr, ds, dop, enh, reinterpret_cast<__nv_bfloat16*>(ximg), nsamples, sm_count, st)) return false;
   if (cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes) != cudaSuccess) {
@@ -1382,7 +1376,6 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   }
   EncParams ep;
   ep.x_images = ximg;
-  ep.h_out = hout;
   ep.layers = w.layers_dev;
   ep.num_layers = w.num_layers;
   ep.activation = activation;
@@ -1394,7 +1387,7 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   count_launch();
   if (!check_launch("encoder_kernel")) return false;
   mark();
-  const bool ok = launch_head_tc(head, w.conv_head, hout, enh, out, nsamples, sm_count, st);
+  const bool ok = launch_head_tc(head, w.conv_head, ximg, enh, out, nsamples, sm_count, st);
   mark();
   return ok;
 }

@@ -177,10 +177,8 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
 
   float* in = reinterpret_cast<float*>(smem + OFF_IN);
   const float* res = reinterpret_cast<const float*>(smem + OFF_OUT);
-  float4 w2[kPatchLen];
-#pragma unroll
-  for (int f = 0; f < kPatchLen; ++f) w2[f] = *reinterpret_cast<const float4*>(p.l2_w + f * kD + lane * 4);
-  const float b2 = lane < kPatchLen ? p.l2_b[lane] : 0.f;
+  float* w2s = reinterpret_cast<float*>(smem + OFF_SCRATCH);   // linear_2 weights, [128][8] (k-major, 6 used); rebuilt per pass:
+                                                               // the scratch area lies inside the planes stack_run overwrites
   uint32_t n_run = 0;
 
   for (int64_t sample = blockIdx.x; sample < nsamples; sample += gridDim.x) {
@@ -188,33 +186,71 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
       const int64_t seq = 2 * sample + part;
       const uint8_t* hs = himg + seq * (int64_t)kXImageBytes;   // encoder output: bf16 operand image (tc_layout.cuh)
       const float* es = enh + seq * (int64_t)kPix;
-      // linear_2 (encoders.py:70), Fold (patch_processors.py:69-71) and the residual (fortitran.py:228)
-      for (int t = warp; t < kS; t += kThreads / 32) {
-        const uint2 hw = *reinterpret_cast<const uint2*>(hs + ximage_offset(t, (lane * 4) & ~7) + (lane & 1) * 8);
-        const float4 hv = make_float4(__uint_as_float(hw.x << 16), __uint_as_float(hw.x & 0xFFFF0000u), __uint_as_float(hw.y << 16),
-                                      __uint_as_float(hw.y & 0xFFFF0000u));
+#ifdef AFT_TC_TIMELINE
+      const bool st_on = blockIdx.x == 0 && n_run == 2 && tid == 0;
+      if (st_on) g_conv_tl[20] = clock64();
+#endif
+      for (int i = tid; i < kD * 8; i += kThreads) {
+        const int k = i >> 3, f = i & 7;
+        w2s[i] = f < kPatchLen ? p.l2_w[f * kD + k] : 0.f;
+      }
+      __syncthreads();
+      // linear_2 (encoders.py:70), Fold (patch_processors.py:69-71) and the residual (fortitran.py:228).  Two threads per
+      // token, one per 64-column chunk of its image row (128 contiguous bytes, fetched with eight 16-byte loads in flight).
+      for (int base = 0; base < 2 * kS; base += kThreads) {
+        const int idx = base + tid;
+        const bool valid = idx < 2 * kS;           // whole warps run the shuffles below; only valid lanes store
+        const int t = valid ? idx >> 1 : 0, hf = idx & 1;
+        const uint8_t* row = hs + hf * kXChunkBytes + t * 128;
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const uint4*>(row + ((u ^ (t & 7)) << 4));
         float acc[kPatchLen];
 #pragma unroll
-        for (int f = 0; f < kPatchLen; ++f) acc[f] = hv.x * w2[f].x + hv.y * w2[f].y + hv.z * w2[f].z + hv.w * w2[f].w;
+        for (int f = 0; f < kPatchLen; ++f) acc[f] = 0.f;
+        const float* wk = w2s + hf * 64 * 8;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-          for (int f = 0; f < kPatchLen; ++f) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], off);
-        if (lane < kPatchLen) {
-          float v = acc[0];
+          for (int j = 0; j < 4; ++j) {
+            const float x0 = __uint_as_float(w[j] << 16), x1 = __uint_as_float(w[j] & 0xFFFF0000u);
+            const float* w0 = wk + (u * 8 + 2 * j) * 8;
+            const float4 a0 = *reinterpret_cast<const float4*>(w0), a1 = *reinterpret_cast<const float4*>(w0 + 8);
+            const float2 b0 = *reinterpret_cast<const float2*>(w0 + 4), b1 = *reinterpret_cast<const float2*>(w0 + 12);
+            acc[0] = fmaf(x0, a0.x, acc[0]); acc[1] = fmaf(x0, a0.y, acc[1]); acc[2] = fmaf(x0, a0.z, acc[2]);
+            acc[3] = fmaf(x0, a0.w, acc[3]); acc[4] = fmaf(x0, b0.x, acc[4]); acc[5] = fmaf(x0, b0.y, acc[5]);
+            acc[0] = fmaf(x1, a1.x, acc[0]); acc[1] = fmaf(x1, a1.y, acc[1]); acc[2] = fmaf(x1, a1.z, acc[2]);
+            acc[3] = fmaf(x1, a1.w, acc[3]); acc[4] = fmaf(x1, b1.x, acc[4]); acc[5] = fmaf(x1, b1.y, acc[5]);
+          }
+        }
 #pragma unroll
-          for (int f = 1; f < kPatchLen; ++f) v = (lane == f) ? acc[f] : v;
-          const int pi = t / kTokW, pj = t - pi * kTokW;
-          const int a = lane / kPatchW, b = lane - a * kPatchW;
+        for (int f = 0; f < kPatchLen; ++f) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 1);
+        // the pair shares the six outputs of the token: thread hf writes patch row... elements 3 hf .. 3 hf + 2
+        const int pi = t / kTokW, pj = t - pi * kTokW;
+#pragma unroll
+        for (int ff = 0; ff < 3; ++ff) {
+          const int f = hf * 3 + ff;
+          const float val = hf ? acc[3 + ff] : acc[ff];
+          const int a = f / kPatchW, b = f - a * kPatchW;
           const int r = kPatchH * pi + a, c = kPatchW * pj + b;
-          in[(r + 1) * kPW + c + 1] = v + b2 + es[r * kGridW + c];
+          if (valid) in[(r + 1) * kPW + c + 1] = val + p.l2_b[f] + es[r * kGridW + c];
         }
       }
       __syncthreads();
+#ifdef AFT_TC_TIMELINE
+      if (st_on) g_conv_tl[21] = clock64();
+#endif
       stack_run(smem, sb, tmem, bar, n_run);                    // fortitran.py:231
+#ifdef AFT_TC_TIMELINE
+      if (st_on) g_conv_tl[22] = clock64();
+#endif
       // torch.complex (fortitran.py:180): this pass owns the real or the imaginary half of every element
       for (int i = tid; i < kPix; i += kThreads) out[(sample * kPix + i) * 2 + part] = res[i];
       __syncthreads();
+#ifdef AFT_TC_TIMELINE
+      if (st_on) g_conv_tl[23] = clock64();
+#endif
     }
   }
   tc_fence_before_sync();
@@ -254,6 +290,7 @@ void conv_tc_dump_timeline() {
   if (cudaMemcpyFromSymbol(t, g_conv_tl, sizeof(t)) != cudaSuccess) return;
   const char* names[] = {"conv1", "conv2 issue", "conv2 wait", "conv2 epilogue", "conv3 issue", "conv3 wait", "conv3 epilogue", "conv4"};
   for (int i = 0; i < 8; ++i) fprintf(stderr, "CONV %-15s %llu\n", names[i], t[i + 1] - t[i]);
+  fprintf(stderr, "CONV head: linear_2+fold %llu | stack %llu | store %llu\n", t[21] - t[20], t[22] - t[21], t[23] - t[22]);
   fprintf(stderr, "CONV frontend: upsample %llu | stack %llu | enh store+tokens %llu | linear_1 %llu\n", t[11] - t[10], t[12] - t[11], t[13] - t[12], t[14] - t[13]);
 #endif
 }

@@ -607,7 +607,7 @@ __device__ __forceinline__ void epi_o_tail(uint32_t tmem, uint32_t sb, int g, in
 // `vec` = shared address of the layer's vector block; `xchg` = shared address of the exchange area.
 constexpr int kLnCols = 128 / kParts, kLnUnits = kLnCols / 8;
 __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec, int which, int t, int q, int part, int lane,
-                                       uint32_t xchg, char* img_out) {
+                                       uint32_t xchg, char* x_images, int out_seq) {
   const int rt = q * 32 + lane, r = t * 128 + rt;
   const uint32_t bias = vec + 4 * ((which == 1 ? kVecBOut : kVecBL2) + part * kLnCols);
   const uint32_t gam = vec + 4 * ((which == 1 ? kVecN1W : kVecN2W) + part * kLnCols);
@@ -674,7 +674,7 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec,
       const uint32_t off = r * 128 + (((u0 + u) ^ (r & 7)) << 4);
       st_shared_v4(sb + OFF_X + (c0 >> 6) * kXChunkBytes + off, pk.x, pk.y, pk.z, pk.w);
       // last layer: the same 16 bytes go to the sequence's image in global memory (the encoder output replaces its input)
-      if (img_out != nullptr) *reinterpret_cast<uint4*>(img_out + (c0 >> 6) * kXChunkBytes + off) = pk;
+      if (out_seq >= 0) *reinterpret_cast<uint4*>(x_images + out_seq * (int64_t)kXImageBytes + (c0 >> 6) * kXChunkBytes + off) = pk;
     }
   }
   // No trailing barrier: consecutive tiles alternate between two exchange areas (see the call sites), and a warp can only
@@ -1009,12 +1009,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
     const uint32_t qkv_bias = miscb + MISC_QKV_BIAS;   // [2][96] f32
     const uint32_t vec = sb + OFF_VEC;                 // the layer's 1024-float vector block
 
+    const int nseq = (int)p.nseq;   // one launch never carries more than 2^31 sequences (aft_api.cu chunks the batch)
 #pragma unroll 1
-    for (int64_t seq = blockIdx.x; seq < p.nseq; seq += gridDim.x, ++n_seq) {
+    for (int seq = blockIdx.x; seq < nseq; seq += gridDim.x, ++n_seq) {
       mbar_wait(misc + MB_X_FULL, n_seq & 1);   // the residual image is read with generic loads by the LayerNorm epilogues
 #pragma unroll 1
       for (int l = 0; l < L; ++l, ++n_layer) {
-        const bool tl = AFT_TL_ON(p.timeline != nullptr && blockIdx.x == 0 && seq == (int64_t)gridDim.x && l == 1 && threadIdx.x == 0);
+        const bool tl = AFT_TL_ON(p.timeline != nullptr && blockIdx.x == 0 && seq == (int)gridDim.x && l == 1 && threadIdx.x == 0);
 #pragma unroll 1
         for (int g = 0; g < 4; ++g, ++n_head) {
           // ---- QKV epilogue of head g: P.V / score tile #k of this CTA has k = 3 * n_head + t, so k & 1 == (n_head + t) & 1
@@ -1165,7 +1166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         tl_event(p, tl, 281, tl_n);   // OUT_DONE seen
 #pragma unroll 1
         for (int t = 0; t < 3; ++t)
-          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 1, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, nullptr);
+          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 1, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, nullptr, -1);
         tc_fence_before_sync();
         fence_proxy_async_smem();
         warp_arrive(misc + MB_X1_READY, lane);
@@ -1201,10 +1202,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         mbar_wait(misc + MB_F2_DONE + 16, 1);
         tc_fence_after_sync();
         tl_event(p, tl, 340, tl_n);   // FFN2 complete seen
-        char* img_out = (l == L - 1) ? p.x_images + seq * (int64_t)kXImageBytes : nullptr;
 #pragma unroll 1
         for (int t = 0; t < 3; ++t)
-          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, img_out);
+          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, p.x_images, l == L - 1 ? seq : -1);
         tc_fence_before_sync();
         fence_proxy_async_smem();
         if (l == L - 1) warp_arrive(misc + MB_X_FREE, lane);

@@ -47,7 +47,8 @@ namespace {
 using namespace ptx;
 
 #ifndef AFT_TC_POLY_EXP
-#define AFT_TC_POLY_EXP 0   // 1: one exponential in four goes through ex2_poly (FMA pipe) instead of MUFU (measured: no gain, both pipes are equally loaded)
+#define AFT_TC_POLY_EXP 4   // N > 0: in the full score tiles one pair of exponentials in N is evaluated on the FMA pipe (packed
+                            // fp32x2 Cody-Waite + cubic, 6 issue slots per value) instead of MUFU (8 pipe cycles per warp instruction)
 #endif
 #ifndef AFT_TC_PARTS
 #define AFT_TC_PARTS 4
@@ -200,6 +201,23 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
+}
+// 2^x for a pair of x <= 0 on the FMA / ALU pipes: x = n + f with |f| <= 0.5 by the 1.5 * 2^23 rounding trick, cubic minimax
+// for 2^f (max relative error 1.9e-4, ten times below the bf16 rounding of P), n added into the exponent field.
+__device__ __forceinline__ f32x2 ex2_poly2(f32x2 x2) {
+  float a, b;
+  unpack2(x2, a, b);
+  const f32x2 xc = pack2(fmaxf(a, -126.0f), fmaxf(b, -126.0f));
+  const f32x2 t2 = add2(xc, pack2(12582912.0f, 12582912.0f));
+  const f32x2 nr = fma2(t2, pack2(-1.0f, -1.0f), pack2(12582912.0f, 12582912.0f));   // -(t - magic) = -n
+  const f32x2 f2 = add2(xc, nr);
+  f32x2 p2 = fma2(f2, pack2(0.05322283f, 0.05322283f), pack2(0.2424649f, 0.2424649f));
+  p2 = fma2(p2, f2, pack2(0.69373846f, 0.69373846f));
+  p2 = fma2(p2, f2, pack2(1.0f, 1.0f));
+  float pa, pb, ta, tb;
+  unpack2(p2, pa, pb);
+  unpack2(t2, ta, tb);
+  return pack2(__int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23)), __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23)));
 }
 __device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
 __device__ __forceinline__ uint32_t pack_bf16_pair(f32x2 v) {
@@ -407,32 +425,41 @@ __device__ __forceinline__ float softmax_exp(float (&v)[kSmCols], float m) {
 __device__ __forceinline__ float softmax_exp_store(uint32_t tmem, int q, int part, float (&v)[kSmCols], float m) {
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_P + part * (kSmCols / 2);
   constexpr int kFull = kSmCols / 16;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const f32x2 negm2 = pack2(-m, -m);
+  f32x2 s2a = pack2(0.f, 0.f), s2b = pack2(0.f, 0.f);
+  // one pair of columns: subtract the row maximum, exponentiate (MUFU, or the FMA pipe for every AFT_TC_POLY_EXP-th pair),
+  // accumulate the row sum, return the packed bf16 pair
+  auto exp_pair = [&](int gp) -> uint32_t {
+    const f32x2 x2 = add2(pack2(v[2 * gp], v[2 * gp + 1]), negm2);
+    f32x2 e2;
+    if (AFT_TC_POLY_EXP > 0 && gp % (AFT_TC_POLY_EXP > 0 ? AFT_TC_POLY_EXP : 1) == (AFT_TC_POLY_EXP > 0 ? AFT_TC_POLY_EXP : 1) - 1) {
+      e2 = ex2_poly2(x2);
+    } else {
+      float a, b;
+      unpack2(x2, a, b);
+      e2 = pack2(ex2(a), ex2(b));
+    }
+    if (gp & 1) s2b = add2(s2b, e2); else s2a = add2(s2a, e2);
+    return pack_bf16_pair(e2);
+  };
 #pragma unroll
   for (int i = 0; i < kFull; ++i) {
-#pragma unroll
-    for (int j = i * 16; j < i * 16 + 16; j += 4) {
-      v[j] = ex2(v[j] - m); v[j + 1] = ex2(v[j + 1] - m); v[j + 2] = ex2(v[j + 2] - m); v[j + 3] = ex2(v[j + 3] - m);
-      s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3];
-    }
     uint32_t pk[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[i * 16 + 2 * j], v[i * 16 + 2 * j + 1]);
+    for (int j = 0; j < 8; ++j) pk[j] = exp_pair(i * 8 + j);
     tmem_st8(taddr + i * 8, pk);
   }
   if (kSmCols % 16) {
-#pragma unroll
-    for (int j = kFull * 16; j < kSmCols; j += 4) {
-      v[j] = ex2(v[j] - m); v[j + 1] = ex2(v[j + 1] - m); v[j + 2] = ex2(v[j + 2] - m); v[j + 3] = ex2(v[j + 3] - m);
-      s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3];
-    }
     uint32_t pk4[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pk4[j] = pack_bf16x2(v[kFull * 16 + 2 * j], v[kFull * 16 + 2 * j + 1]);
+    for (int j = 0; j < 4; ++j) pk4[j] = exp_pair(kFull * 8 + j);
     tmem_st4(taddr + kFull * 8, pk4);
   }
   tmem_wait_st();
-  return (s0 + s1) + (s2 + s3);
+  float sa, sb2, sc, sd;
+  unpack2(s2a, sa, sb2);
+  unpack2(s2b, sc, sd);
+  return (sa + sb2) + (sc + sd);
 }
 // (3) P tile -> TMEM as bf16 pairs (A operand of P.V): kSmCols / 2 packed columns per thread
 __device__ __forceinline__ void softmax_store(uint32_t tmem, int q, int part, const float (&v)[kSmCols]) {

@@ -47,7 +47,7 @@ namespace {
 using namespace ptx;
 
 #ifndef AFT_TC_POLY_EXP
-#define AFT_TC_POLY_EXP 4   // N > 0: in the full score tiles one pair of exponentials in N is evaluated on the FMA pipe (packed
+#define AFT_TC_POLY_EXP 3   // N > 0: in the full score tiles one pair of exponentials in N is evaluated on the FMA pipe (packed
                             // fp32x2 Cody-Waite + cubic, 6 issue slots per value) instead of MUFU (8 pipe cycles per warp instruction)
 #endif
 #ifndef AFT_TC_PARTS
@@ -197,6 +197,11 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
@@ -224,6 +229,18 @@ __device__ __forceinline__ uint32_t pack_bf16_pair(f32x2 v) {
   float lo, hi;
   unpack2(v, lo, hi);
   return pack_bf16x2(lo, hi);
+}
+// gelu_tanh for a pair (packed arithmetic around the two MUFU.TANH)
+__device__ __forceinline__ f32x2 gelu_tanh2(f32x2 x) {
+  const f32x2 x2 = mul2(x, x);
+  const f32x2 u = mul2(x, fma2(x2, fma2(x2, pack2(-3.51516789e-4f, -3.51516789e-4f), pack2(3.70056460e-2f, 3.70056460e-2f)),
+                               pack2(7.97507884e-1f, 7.97507884e-1f)));
+  float ua, ub, ta, tb;
+  unpack2(u, ua, ub);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ua));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(ub));
+  const f32x2 hx = mul2(x, pack2(0.5f, 0.5f));
+  return fma2(hx, pack2(ta, tb), hx);
 }
 __device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
   lo = __uint_as_float(w << 16);
@@ -375,13 +392,13 @@ __device__ __forceinline__ void epi_qkv_store(uint32_t sb, uint32_t bias96, int 
   for (int i = 0; i < kQkvUnits; ++i) {
     const int u8 = part * kQkvUnits + i;     // unit index inside [q | k | v]
     const int mat = u8 >> 2, u = u8 & 3;     // which matrix, which 16-byte unit of its 64-byte row
-    const float4 b0 = lds_f4(bias96 + u8 * 32), b1 = lds_f4(bias96 + u8 * 32 + 16);
+    const uint4 b0 = ld_shared_v4(bias96 + u8 * 32), b1 = ld_shared_v4(bias96 + u8 * 32 + 16);
     const uint32_t* a = acc + i * 8;
-    st_shared_v4(sb + OFF_QKV + mat * kQkvPart + r * 64 + ((u ^ sw) << 4),
-                 pack_bf16x2(__uint_as_float(a[0]) + b0.x, __uint_as_float(a[1]) + b0.y),
-                 pack_bf16x2(__uint_as_float(a[2]) + b0.z, __uint_as_float(a[3]) + b0.w),
-                 pack_bf16x2(__uint_as_float(a[4]) + b1.x, __uint_as_float(a[5]) + b1.y),
-                 pack_bf16x2(__uint_as_float(a[6]) + b1.z, __uint_as_float(a[7]) + b1.w));
+    auto sum = [](uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
+      return pack_bf16_pair(add2(pack2(__uint_as_float(x0), __uint_as_float(x1)), pack2(__uint_as_float(y0), __uint_as_float(y1))));
+    };
+    st_shared_v4(sb + OFF_QKV + mat * kQkvPart + r * 64 + ((u ^ sw) << 4), sum(a[0], a[1], b0.x, b0.y), sum(a[2], a[3], b0.z, b0.w),
+                 sum(a[4], a[5], b1.x, b1.y), sum(a[6], a[7], b1.z, b1.w));
   }
 }
 
@@ -710,28 +727,41 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec,
 
 // FFN1 accumulators (pair pr = hidden units 128 pr .. 128 pr + 127, one row tile), split over the warpgroups: load + bias
 constexpr int kActCols = 128 / kParts;
-__device__ __forceinline__ void act_load(uint32_t tmem, uint32_t vec, int pr, int q, int part, float (&f)[kActCols]) {
+__device__ __forceinline__ void act_load(uint32_t tmem, uint32_t vec, int pr, int q, int part, f32x2 (&f)[kActCols / 2]) {
   const uint32_t bias = vec + 4 * (kVecBL1 + pr * 128 + part * kActCols);
   uint32_t a[kActCols];
   tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_F1 + part * kActCols, a);
   tmem_wait_ld();
 #pragma unroll
   for (int u = 0; u < kActCols / 4; ++u) {
-    const float4 b = lds_f4(bias + u * 16);
-    f[u * 4] = __uint_as_float(a[u * 4]) + b.x; f[u * 4 + 1] = __uint_as_float(a[u * 4 + 1]) + b.y;
-    f[u * 4 + 2] = __uint_as_float(a[u * 4 + 2]) + b.z; f[u * 4 + 3] = __uint_as_float(a[u * 4 + 3]) + b.w;
+    const uint4 b = ld_shared_v4(bias + u * 16);
+    f[u * 2] = add2(pack2(__uint_as_float(a[u * 4]), __uint_as_float(a[u * 4 + 1])), pack2(__uint_as_float(b.x), __uint_as_float(b.y)));
+    f[u * 2 + 1] = add2(pack2(__uint_as_float(a[u * 4 + 2]), __uint_as_float(a[u * 4 + 3])), pack2(__uint_as_float(b.z), __uint_as_float(b.w)));
   }
 }
 // GELU / ReLU -> bf16 -> hidden images (K-chunks of FFN2's A operand): the pair's first 64 units go to buffer 0, the
 // others to buffer 1.  Padding rows 280..287 are not written (the O region's padding rows hold scratch data).
-__device__ __forceinline__ void act_store(uint32_t sb, int t, int act, int q, int part, int lane, float (&f)[kActCols]) {
+__device__ __forceinline__ void act_store(uint32_t sb, int t, int act, int q, int part, int lane, f32x2 (&f)[kActCols / 2]) {
   const int r = t * 128 + q * 32 + lane;
+  uint32_t pk[kActCols / 2];
   if (act == AFT_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < kActCols; ++j) f[j] = AFT_TC_GELU_TANH ? gelu_tanh(f[j]) : gelu_fast(f[j]);
+    for (int j = 0; j < kActCols / 2; ++j) {
+      if (AFT_TC_GELU_TANH) {
+        pk[j] = pack_bf16_pair(gelu_tanh2(f[j]));
+      } else {
+        float a, b;
+        unpack2(f[j], a, b);
+        pk[j] = pack_bf16x2(gelu_fast(a), gelu_fast(b));
+      }
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < kActCols; ++j) f[j] = fmaxf(f[j], 0.f);
+    for (int j = 0; j < kActCols / 2; ++j) {
+      float a, b;
+      unpack2(f[j], a, b);
+      pk[j] = pack_bf16x2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+    }
   }
   const int c0 = part * kActCols;                       // first column inside the 128-wide pair
   const uint32_t row = sb + OFF_O + (c0 >> 6) * kHidBytes + r * 128;
@@ -739,8 +769,7 @@ __device__ __forceinline__ void act_store(uint32_t sb, int t, int act, int q, in
   if (r < kS) {
 #pragma unroll
     for (int u = 0; u < kActCols / 8; ++u)
-      st_shared_v4(row + (((u0 + u) ^ (r & 7)) << 4), pack_bf16x2(f[8 * u], f[8 * u + 1]),
-                   pack_bf16x2(f[8 * u + 2], f[8 * u + 3]), pack_bf16x2(f[8 * u + 4], f[8 * u + 5]), pack_bf16x2(f[8 * u + 6], f[8 * u + 7]));
+      st_shared_v4(row + (((u0 + u) ^ (r & 7)) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
   }
 }
 
@@ -1208,7 +1237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           tc_fence_after_sync();
           tl_event(p, tl, 300 + k, tl_n);   // F1_DONE(k) seen
           if (active) {   // accumulators defined and consumed inside one branch (see the softmax tiles)
-            float f[kActCols];
+            f32x2 f[kActCols / 2];
             act_load(tmem, vec, pr, q, part, f);
             tc_fence_before_sync();
             warp_arrive(misc + MB_F1_FREE, lane);

@@ -264,9 +264,10 @@ __global__ void conv_tc_pack_kernel(ConvPack src, uint8_t* __restrict__ dst) {
   __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(dst + kPkW2);
   __nv_bfloat16* w3 = reinterpret_cast<__nv_bfloat16*>(dst + kPkW3);
   float* f = reinterpret_cast<float*>(dst + kPkF32);
-  if (i < 9 * 512) {           // conv2: [tap][half][cout 32][8]; half 1 (input channels 8..15) is zero
-    const int t = i / 512, rem = i % 512, half = rem / 256, co = (rem % 256) / 8, j = rem % 8;
-    w2[i] = __float2bfloat16(half == 0 ? src.w1[(t * 8 + j) * 32 + co] : 0.f);   // src.w1 is [tap][cin 8][cout 32]
+  if (i < 5 * 512) {           // conv2: [tap pair][half = tap of the pair][cout 32][cin 8]; the tenth tap is zero
+    const int pr = i / 512, rem = i % 512, half = rem / 256, co = (rem % 256) / 8, j = rem % 8;
+    const int t = 2 * pr + half;
+    w2[i] = __float2bfloat16(t < 9 ? src.w1[(t * 8 + j) * 32 + co] : 0.f);   // src.w1 is [tap][cin 8][cout 32]
   }
   if (i < 18 * 256) {          // conv3: [tap][kstep][half][cout 16][8]; couts 8..15 are zero
     const int tk = i / 256, rem = i % 256, half = rem / 128, co = (rem % 128) / 8, j = rem % 8;

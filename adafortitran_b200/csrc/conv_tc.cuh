@@ -11,7 +11,8 @@
 // channels) with a shifted start address -- no im2col copy.  M tiles run over padded positions (16 tiles of 128);
 // results at border positions are discarded (written back as the zeros the next layer's padding needs).
 //
-//   conv2:  A = a1 planes (8 channels + 8 zero channels = K 16), B = [32 cout][16] per tap    ->  9 MMAs / tile, N = 32
+//   conv2:  A = a1 plane, K 16 = 8 channels x 2 taps (the descriptor's LBO is the position offset between the two taps),
+//           B = [32 cout][2 taps x 8 cin] per tap pair                                         ->  5 MMAs / tile, N = 32
 //   conv3:  A = mid planes (32 channels = 2 K-steps),            B = [8+8 zero cout][16]       -> 18 MMAs / tile, N = 16
 // Accumulators: conv2 fills all 512 TMEM columns (16 tiles x 32), conv3 reuses the first 256.
 #pragma once
@@ -32,7 +33,7 @@ constexpr int kPlaneBytes = kPosAlloc * 16;   // one 8-channel group: 33,792 byt
 constexpr int kTiles = 16;
 
 // packed parameters of one conv stack (global memory, built by conv_tc_pack): byte offsets
-constexpr int kPkW2 = 0;                      // 9 taps x [2 halves][32 cout][8] bf16 = 9 x 1024
+constexpr int kPkW2 = 0;                      // 5 tap pairs x [2 taps][32 cout][8 cin] bf16 = 5 x 1024 (tap 9 = zeros)
 constexpr int kPkW3 = 9216;                   // 18 (tap, kstep) x [2 halves][16 cout][8] bf16 = 18 x 512
 constexpr int kPkF32 = 18432;                 // fp32: w0[9][8] | b0[8] | b1[32] | b2[8] | w3[9][8] | b3[1] (+pad) = 200 floats
 constexpr int kPkBytes = 18432 + 800;         // 19,232
@@ -118,18 +119,23 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   __syncthreads();
   AFT_CONV_STAMP(1);
 
-  // ---- conv2 (8 -> 32) on the tensor core: 16 tiles x 9 taps, K = 16 (8 channels + 8 zero channels)
+  // ---- conv2 (8 -> 32) on the tensor core: 16 tiles x 5 tap pairs, K = 16 (8 channels x 2 taps)
   if (warp == 0) {   // converged warp, elected lane issues (keeps the descriptor math in uniform registers)
     const bool el = elect_one();
     tc_fence_after_sync();
-    const uint32_t a_lo = desc_lo_none(sb + OFF_A1 + kPosGuard * 16, kPlaneBytes);   // + positions (16 B each == 1 address unit)
+    // K = 16 holds the 8 input channels of TWO taps: the second K half of the A descriptor (LBO) is the same plane seen
+    // through the next tap, i.e. (shift(t1) - shift(t0)) positions further.  Five MMAs per tile (the ninth tap is paired
+    // with zero weights) instead of nine.
+    const uint32_t a_base = ((sb + OFF_A1 + kPosGuard * 16) >> 4) & 0x3FFF;   // + positions (16 B each == 1 address unit)
     const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW2, 512);
 #pragma unroll 1
     for (int i = 0; i < kTiles; ++i)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int shift = (t / 3 - 1) * kPW + (t % 3 - 1);
-        mma_ss(tmem + i * 32, desc_join(a_lo + i * 128 + shift), desc_join(b_lo + t * 64), kIdescConv2, t > 0, el);
+      for (int pr = 0; pr < 5; ++pr) {
+        const int t0 = 2 * pr, t1 = pr < 4 ? 2 * pr + 1 : 2 * pr;
+        const int shift0 = (t0 / 3 - 1) * kPW + (t0 % 3 - 1), shift1 = (t1 / 3 - 1) * kPW + (t1 % 3 - 1);
+        const uint32_t lbo = pr < 4 ? (uint32_t)(shift1 - shift0) : 1u;        // in 16-byte units
+        mma_ss(tmem + i * 32, desc_join((a_base + i * 128 + shift0) | (lbo << 16)), desc_join(b_lo + pr * 64), kIdescConv2, pr > 0, el);
       }
     mma_commit(bar, el);
   }

@@ -49,8 +49,33 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every ``csrc/*.cu`` for sm_100a and link ``libaft_b200.so``.  Returns its path."""
+VARIANTS = {
+    # name -> extra nvcc defines.  "chaos": every mbarrier wait of the tensor-core kernels is preceded by a pseudo-random
+    # delay (tc_ptx.cuh), which shakes the relative timing of the kernel's roles; used by the protocol test
+    # (tests/test_gpu_bf16.py::test_protocol_under_random_delays) through AFT_B200_LIB.
+    "chaos": ["-DAFT_TC_CHAOS"],
+}
+
+
+def lib_file(variant: str | None = None) -> str:
+    return LIB if not variant else os.path.join(LIB_DIR, f"libaft_b200_{variant}.so")
+
+
+def build(force: bool = False, verbose: bool = False, variant: str | None = None) -> str:
+    """Compile every ``csrc/*.cu`` for sm_100a and link ``libaft_b200.so`` (or a named variant).  Returns its path."""
+    global OBJ, LIB
+    if variant:
+        saved = (OBJ, LIB, os.environ.get("AFT_NVCC_DEFS"))
+        OBJ, LIB = os.path.join(PKG, f"build_{variant}"), lib_file(variant)
+        os.environ["AFT_NVCC_DEFS"] = " ".join(_extra_defs() + VARIANTS[variant])
+        try:
+            return build(force=force, verbose=verbose)
+        finally:
+            OBJ, LIB = saved[0], saved[1]
+            if saved[2] is None:
+                os.environ.pop("AFT_NVCC_DEFS", None)
+            else:
+                os.environ["AFT_NVCC_DEFS"] = saved[2]
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -95,4 +120,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var))

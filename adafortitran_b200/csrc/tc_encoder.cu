@@ -101,15 +101,13 @@ enum : uint32_t {
   MB_P_READY = 120,    // warp  : P tile written to TMEM
   MB_PV_DONE = 128,    // commit: P.V complete (P columns free, O accumulator valid)
   MB_O_FREE = 136,     // 2 x warp : O accumulator buffer b read out, O image columns written
-  MB_OUT_DONE = 152,   // commit: out_proj accumulators complete
-  MB_X1_READY = 160,   // warp  : LayerNorm1 written to X
+                       // (152, 160, 224: free -- the per-tile OUT_DONE / X1_READY / X2_READY barriers live in the second block)
   MB_F1_DONE = 168,    // commit: FFN1 accumulator tile (128 rows x 128 hidden units) complete
   MB_F1_FREE = 176,    // warp  : FFN1 accumulator tile read out
   MB_F2_DONE = 184,    // 3 x commit: FFN2 partial product of row tile t complete (hidden rows of the tile free / final result)
   MB_HID_READY = 208,  // 2 x warp : hidden image rows of FFN tile k (two 64-unit chunks) complete, barrier k & 1.  Two barriers:
                        // FFN1(k+1) is issued before the issuer waits for tile k, so a single barrier could collect a fast
                        // warp's arrival for tile k+1 while a slow warp still owes the one for tile k
-  MB_X2_READY = 224,   // warp  : LayerNorm2 written to X
   MB_VEC_FULL = 232,   // commit: per-layer vector block landed in shared memory
   MB_BIAS_FULL = 240,  // 2 x commit: in_proj bias of head g landed in buffer g & 1
   MB_COUNT_BYTES = 256,
@@ -135,6 +133,17 @@ constexpr uint32_t OFF_XT_MAX = OFF_O + 280 * 128, OFF_XT_SUM = OFF_XT_MAX + 512
 // when that region is dead (O image consumed by out_proj / hidden images consumed by FFN2, next writer behind a full
 // X1_READY / X2_READY hand-shake).
 constexpr uint32_t OFF_LN_XCHG = OFF_O;
+// LayerNorm1 cannot use it: FFN1 of row tile 0 starts as soon as LayerNorm1 has released that tile, so fast warps may
+// already store hidden rows into the O region while others are still in LayerNorm1.  Its second area is the tail of the
+// in_proj slot: bytes [16 K, 24 K) are only written by the 24 KB head slices, which are not in flight between the last
+// head's projection and the end of FFN1.
+constexpr uint32_t OFF_LN1_XCHG = OFF_W + 16384;
+// Second mbarrier block: the padding rows 280..287 of the O region's second chunk (never written: the epilogues skip
+// padding rows, the tensor core only reads them into padding rows of its results).  Per-row-tile hand-offs:
+constexpr uint32_t OFF_BAR2 = OFF_O + kXChunkBytes + 280 * 128;
+constexpr uint32_t MB2_OUT_DONE = 0;    // 3 x commit: out_proj accumulators of row tile t complete
+constexpr uint32_t MB2_X1_READY = 24;   // 3 x warp  : LayerNorm1 rows of tile t written to X
+constexpr uint32_t MB2_X2_READY = 48;   // 3 x warp  : LayerNorm2 rows of tile t written to X, accumulator columns of the tile free
 
 
 __device__ __forceinline__ float ex2(float x) {
@@ -822,11 +831,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
   if (threadIdx.x == 0) {
     const uint32_t commit_bars[] = {MB_VEC_FULL, MB_BIAS_FULL, MB_BIAS_FULL + 8, MB_X_FULL, MB_ATTN_DONE, MB_W_FULL, MB_W_FULL + 8, MB_W_FULL + 16, MB_W_FULL + 24,
                                     MB_W_EMPTY, MB_W_EMPTY + 8, MB_W_EMPTY + 16, MB_W_EMPTY + 24, MB_QKV_DONE, MB_S_DONE,
-                                    MB_PV_DONE, MB_OUT_DONE, MB_F1_DONE, MB_F2_DONE, MB_F2_DONE + 8, MB_F2_DONE + 16};
-    const uint32_t warp_bars[] = {MB_X_FREE, MB_QKV_READY, MB_S_LOADED, MB_P_READY, MB_O_FREE, MB_O_FREE + 8, MB_X1_READY,
-                                  MB_F1_FREE, MB_HID_READY, MB_HID_READY + 8, MB_X2_READY};
+                                    MB_PV_DONE, MB_F1_DONE, MB_F2_DONE, MB_F2_DONE + 8, MB_F2_DONE + 16};
+    const uint32_t warp_bars[] = {MB_X_FREE, MB_QKV_READY, MB_S_LOADED, MB_P_READY, MB_O_FREE, MB_O_FREE + 8,
+                                  MB_F1_FREE, MB_HID_READY, MB_HID_READY + 8};
     for (uint32_t b : commit_bars) mbar_init(misc + b, 1);
     for (uint32_t b : warp_bars) mbar_init(misc + b, kComputeWarps);
+    for (uint32_t t = 0; t < 3; ++t) {
+      mbar_init(sb + OFF_BAR2 + MB2_OUT_DONE + 8 * t, 1);
+      mbar_init(sb + OFF_BAR2 + MB2_X1_READY + 8 * t, kComputeWarps);
+      mbar_init(sb + OFF_BAR2 + MB2_X2_READY + 8 * t, kComputeWarps);
+    }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(miscb + MISC_TMEM_PTR, 512); tmem_relinquish(); }
@@ -897,7 +911,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
       // The whole warp runs the schedule converged (all lanes poll the barriers, addresses stay warp-uniform and live in
       // uniform registers); only the tcgen05.mma / tcgen05.commit instructions are predicated on the elected lane.
       const bool el = elect_one();
-      Phase x_full, x2_ready, qkv_ready, s_loaded, p_ready, x1_ready;
+      Phase x_full, qkv_ready, s_loaded, p_ready;
+      const uint32_t bar2 = sb + OFF_BAR2;
       uint32_t n_in = 0, ring_base = 0, n_pv = 0, n_f1 = 0, n_layers_done = 0, tl_n = 0;
       // ring entry `idx` (global index): wait until it is resident, return its address; release = commit its empty barrier
       auto ring_wait = [&](uint32_t idx) -> uint32_t {
@@ -911,9 +926,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         x_full.wait(misc + MB_X_FULL);
         for (int l = 0; l < L; ++l, ++n_layers_done, ring_base += 8) {
           const bool tl = AFT_TL_ON(p.timeline != nullptr && blockIdx.x == 0 && seq == (int64_t)gridDim.x && l == 1 && lane == 0);
-          // X and the accumulator columns [0,384) are free once the previous LayerNorm2 has finished
-          if (n_layers_done > 0) x2_ready.wait(misc + MB_X2_READY);
-          tc_fence_after_sync();
           // QKV projection of head g, row tiles [t0, t1); accumulators alias the S columns.  `first` waits for the weight
           // slice, `last` releases it and publishes the accumulators.
           auto issue_qkv = [&](int g, int t0, int t1, bool first, bool last) {
@@ -931,7 +943,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               ++n_in;
             }
           };
-          issue_qkv(0, 0, 3, true, true);
+          // Head 0: row tile t of X and the accumulator columns the tile's projection overwrites are free once the
+          // previous LayerNorm2 has finished tiles 0..t (per-tile barriers, one completion per layer each).  Inside a
+          // sequence the projection follows LayerNorm2 tile by tile; the first layer of a sequence starts from a new image.
+          if (n_layers_done > 0 && l > 0) {
+            for (int t = 0; t < 3; ++t) {
+              mbar_wait(bar2 + MB2_X2_READY + 8 * t, (n_layers_done - 1) & 1);
+              tc_fence_after_sync();
+              issue_qkv(0, t, t + 1, t == 0, t == 2);
+            }
+          } else {
+            if (n_layers_done > 0)
+              for (int t = 0; t < 3; ++t) mbar_wait(bar2 + MB2_X2_READY + 8 * t, (n_layers_done - 1) & 1);
+            tc_fence_after_sync();
+            issue_qkv(0, 0, 3, true, true);
+          }
           for (int g = 0; g < 4; ++g) {
             // ---- attention of head g
             qkv_ready.wait(misc + MB_QKV_READY);
@@ -980,23 +1006,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             mbar_wait(misc + MB_O_FREE + 8 * ((n_pv + 1) & 1), (((n_pv + 1) >> 1) - 1) & 1);
             tc_fence_after_sync();
             tl_event(p, tl, 160, tl_n);   // out_proj issue start
-            const uint32_t w0 = ring_wait(ring_base + 0);
-            for (int t = 0; t < 3; ++t)
+            const uint32_t w0 = ring_wait(ring_base + 0), w1 = ring_wait(ring_base + 1);
+            for (int t = 0; t < 3; ++t) {   // tile-major: LayerNorm1 of tile 0 starts while tiles 1 and 2 are still in the pipe
               issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + t * 128 * 128, 0, w0, 0, 4, kIdescN128, false, el);
-            ring_release(ring_base + 0);
-            const uint32_t w1 = ring_wait(ring_base + 1);
-            for (int t = 0; t < 3; ++t)
               issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + kXChunkBytes + t * 128 * 128, 0, w1, 0, 4, kIdescN128, true, el);
+              mma_commit(bar2 + MB2_OUT_DONE + 8 * t, el);
+            }
+            ring_release(ring_base + 0);
             ring_release(ring_base + 1);
-            mma_commit(misc + MB_OUT_DONE, el);
             tl_event(p, tl, 161, tl_n);   // out_proj issued
           }
           // ---- FFN.  FFN1 runs as N = 128 MMAs over pairs of hidden chunks (tile k = 3 pr + t, single accumulator tile in
           // TMEM); the FFN2 partial products of row tile t are issued as soon as the GELU of that tile is stored, right
           // behind the next FFN1 tile.  W1 pair: K-chunk 0 in a ring slot, K-chunk 1 in the in_proj slot.
-          x1_ready.wait(misc + MB_X1_READY);
-          tc_fence_after_sync();
-          tl_event(p, tl, 170, tl_n);   // X1_READY seen
+          tl_event(p, tl, 170, tl_n);   // FFN start
           {
             constexpr uint32_t kHi = (uint32_t)(desc_k_sw128_const() >> 32);
             auto desc128 = [&](uint32_t saddr) -> uint32_t { return (uint32_t)desc_k_sw128_const() | ((saddr >> 4) & 0x3FFF); };
@@ -1028,6 +1051,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
                 tc_fence_after_sync();
                 w1b = sb + OFF_W;
               }
+              if (pr == 0) mbar_wait(bar2 + MB2_X1_READY + 8 * t, n_layers_done & 1);   // LayerNorm1 rows of this tile are in X
               if (n_f1 >= 1) mbar_wait(misc + MB_F1_FREE, (n_f1 - 1) & 1);
               tc_fence_after_sync();
               {
@@ -1217,15 +1241,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         // ---- out_proj epilogue: + bias + residual -> LayerNorm1 -> X
         tl_event(p, tl, 280, tl_n);   // waiting OUT_DONE
         mbar_wait(misc + MB_VEC_FULL, n_layer & 1);   // this layer's bias / LayerNorm vectors are in shared memory
-        mbar_wait(misc + MB_OUT_DONE, n_layer & 1);
-        tc_fence_after_sync();
-        tl_event(p, tl, 281, tl_n);   // OUT_DONE seen
 #pragma unroll 1
-        for (int t = 0; t < 3; ++t)
-          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 1, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, nullptr, -1);
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
-        warp_arrive(misc + MB_X1_READY, lane);
+        for (int t = 0; t < 3; ++t) {   // per row tile: out_proj accumulators in -> LayerNorm1 rows out (FFN1 of the tile may start)
+          if (t < 2 || tile2_active) {
+            mbar_wait(sb + OFF_BAR2 + MB2_OUT_DONE + 8 * t, n_layer & 1);
+            tc_fence_after_sync();
+            epi_ln(tmem, sb, vec, 1, t, q, part, lane, t == 1 ? sb + OFF_LN1_XCHG : miscb + MISC_XMAX, nullptr, -1);
+          }
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          warp_arrive(sb + OFF_BAR2 + MB2_X1_READY + 8 * t, lane);
+        }
         tl_event(p, tl, 282, tl_n);   // LayerNorm1 done
         // ---- FFN1 epilogues: bias + GELU -> hidden images.  Tile k = 3 pr + t of this layer: F1_DONE / F1_FREE / HID_READY
         // complete six times per layer (phase parity k & 1), F2_DONE[t] twice (pair 0: rows free again, pair 1: final).
@@ -1253,18 +1279,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           warp_arrive(misc + MB_HID_READY + 8 * (k & 1), lane);
         }
         // ---- linear2 epilogue: + bias + residual -> LayerNorm2 -> X (+ fp32 result after the last layer)
-        mbar_wait(misc + MB_F2_DONE, 1);        // second completion of each tile's barrier in this layer (in issue order:
-        mbar_wait(misc + MB_F2_DONE + 8, 1);    // the last one covers them all, the others return at once)
-        mbar_wait(misc + MB_F2_DONE + 16, 1);
-        tc_fence_after_sync();
-        tl_event(p, tl, 340, tl_n);   // FFN2 complete seen
+        tl_event(p, tl, 340, tl_n);   // LayerNorm2 start
 #pragma unroll 1
-        for (int t = 0; t < 3; ++t)
-          if (t < 2 || tile2_active) epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, p.x_images, l == L - 1 ? seq : -1);
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
+        for (int t = 0; t < 3; ++t) {   // per row tile: second completion of the tile's F2_DONE in this layer = final accumulators
+          if (t < 2 || tile2_active) {
+            mbar_wait(misc + MB_F2_DONE + 8 * t, 1);
+            tc_fence_after_sync();
+            epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, p.x_images, l == L - 1 ? seq : -1);
+          }
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          warp_arrive(sb + OFF_BAR2 + MB2_X2_READY + 8 * t, lane);
+        }
         if (l == L - 1) warp_arrive(misc + MB_X_FREE, lane);
-        warp_arrive(misc + MB_X2_READY, lane);
         tl_event(p, tl, 341, tl_n);   // LayerNorm2 done
       }
     }

@@ -145,3 +145,24 @@ def test_empty_batch_and_profile_api(sd):
         _capi.check(lib.aft_profile_read(m._handle, ms, nl))
         assert lib.aft_launch_count() - n0 == 3 and list(nl) == [1, 1, 1] and all(t > 0 for t in ms)
         _capi.check(lib.aft_profile_enable(m._handle, 0))
+
+
+def test_protocol_under_random_delays():
+    """The encoder / conv kernels are static programs of several roles that meet only through mbarriers.  The "chaos"
+    build (adafortitran_b200.build variant, built by __graft_entry__.build) delays every wait by a pseudo-random time, so
+    a hand-off that only works because of the usual relative timing shows up as a wrong result or a trapped wait."""
+    import json, os, subprocess, sys
+    from adafortitran_b200.build import lib_file
+    lib = lib_file("chaos")
+    if not os.path.exists(lib):
+        pytest.skip("chaos variant not built (python -m adafortitran_b200.build --variant=chaos)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AFT_B200_LIB=lib)
+    for batch, kind, gate in (("296", "forti", -45.0), ("74", "ada", -36.0)):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "chaos_check.py"), batch, kind], env=env,
+                           capture_output=True, text=True, timeout=900)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        assert line, r.stdout + r.stderr
+        res = json.loads(line[-1])
+        assert r.returncode == 0, res
+        assert res["lib"] == "libaft_b200_chaos.so" and res["wait_timeouts"] == 0 and res["rel_db_bf16_vs_fp32"] <= gate, res

@@ -20,6 +20,9 @@ while i < len(per):
         segs.append(cur)
         m = re.search(r'\+0x([0-9a-f]+)\]', ins)
         bar = int(m.group(1), 16) - 0x37b00 if m else None
+        if bar is not None and bar < 0:   # second barrier block (OFF_BAR2 = 0x11c00): per-row-tile hand-offs
+            b2 = bar + 0x37b00 - 0x11c00
+            bar = ("OUT_DONE[%d]" % (b2 // 8)) if b2 < 24 else ("X1_READY[%d]" % ((b2 - 24) // 8)) if b2 < 48 else ("X2_READY[%d]" % ((b2 - 48) // 8))
         label = ('wait ' + str(names.get(bar, bar))) if 'TRYWAIT' in ins else 'bar.sync'
         w = s
         # the spin loop: following instructions up to and including the backward branch

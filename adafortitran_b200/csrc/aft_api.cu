@@ -505,6 +505,25 @@ int aft_error_sums(const void* est, const void* truth, int64_t count, double* su
                            static_cast<cudaStream_t>(stream)) ? AFT_OK : AFT_ERR_CUDA;
 }
 
+int aft_extract_pilots(const void* ls_grid, void* pilots, int32_t* counts, int64_t batch, int32_t cells, int32_t expected, void* stream) {
+  if (batch < 0 || cells <= 0 || expected <= 0 || expected > cells || (batch > 0 && (!ls_grid || !pilots || !counts))) {
+    set_error("aft_extract_pilots: bad argument");
+    return AFT_ERR_INVALID;
+  }
+  return launch_extract_pilots(static_cast<const float2*>(ls_grid), static_cast<float2*>(pilots), counts, batch, cells, expected,
+                               static_cast<cudaStream_t>(stream)) ? AFT_OK : AFT_ERR_CUDA;
+}
+
+int aft_linear_forward(const float* weight, const float* bias, const float* x, float* y, int64_t batch, int32_t in_dim, int32_t out_dim,
+                       void* stream) {
+  if (batch < 0 || in_dim <= 0 || out_dim <= 0 || !weight || !bias || (batch > 0 && (!x || !y))) {
+    set_error("aft_linear_forward: bad argument");
+    return AFT_ERR_INVALID;
+  }
+  if (in_dim > 4096) { set_error("aft_linear_forward: in_dim %d not supported (<= 4096)", in_dim); return AFT_ERR_UNSUPPORTED; }
+  return launch_linear(weight, bias, x, y, batch, in_dim, out_dim, static_cast<cudaStream_t>(stream)) ? AFT_OK : AFT_ERR_CUDA;
+}
+
 int aft_profile_enable(AftHandle* h, int enable) {
   if (!h) { set_error("aft_profile_enable: NULL handle"); return AFT_ERR_INVALID; }
   h->profile = enable != 0;

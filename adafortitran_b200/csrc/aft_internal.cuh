@@ -117,6 +117,10 @@ bool launch_gemm_f32(int epi, const float* A, const float* W, const float* bias,
 // attn_f32.cu : per (sequence, head) softmax(q k^T / sqrt(dh)) v, fp32
 bool launch_attn_f32(const float* qkv, float* out, int64_t nseq, cudaStream_t st);
 
+// aux.cu : "next" rows N2 / N3 -- pilot extraction from the sparse LS grid, LinearEstimator
+bool launch_extract_pilots(const float2* grid, float2* pilots, int32_t* counts, int64_t batch, int cells, int expected, cudaStream_t st);
+bool launch_linear(const float* w, const float* bias, const float* x, float* y, int64_t batch, int in_dim, int out_dim, cudaStream_t st);
+
 // reduce.cu
 bool launch_error_sums(const float2* est, const float2* truth, int64_t count, double* sums, cudaStream_t st);
 

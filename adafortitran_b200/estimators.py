@@ -422,3 +422,43 @@ class AdaFortiTranEstimator(BaseFortiTranEstimator):
 
     def __init__(self, system_config: SystemConfig, model_config: ModelConfig) -> None:
         super().__init__(system_config, model_config, use_channel_adaptation=True)
+
+
+class LinearEstimator(nn.Module):
+    """Learned linear estimator ``h_hat = W h_pilot + b`` (reference src/models/linear.py:15-107): same constructor,
+    attributes, ``state_dict`` keys (``linear.weight`` [out, in], ``linear.bias``) and shape check; the product runs in
+    ``aft_linear_forward``.  Like the reference's ``nn.Linear`` it is a real-valued map: complex input is rejected."""
+
+    def __init__(self, system_config: SystemConfig, model_config: ModelConfig) -> None:
+        super().__init__()
+        self.system_config = system_config
+        self.model_config = model_config
+        self.device = torch.device(model_config.device)
+        self.logger = logging.getLogger(__name__)
+        self.ofdm_size = (system_config.ofdm.num_scs, system_config.ofdm.num_symbols)
+        self.pilot_size = (system_config.pilot.num_scs, system_config.pilot.num_symbols)
+        self.linear = nn.Linear(self.pilot_size[0] * self.pilot_size[1], self.ofdm_size[0] * self.ofdm_size[1])
+        self.to(self.device)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        expected = (x.size(0), self.pilot_size[0], self.pilot_size[1])
+        if tuple(x.size()) != expected:
+            raise ValueError(f"Expected input shape {expected}, got {tuple(x.size())}")     # linear.py:76-80
+        if x.is_complex():
+            raise RuntimeError("LinearEstimator is a real-valued nn.Linear: complex input has no defined result "
+                               "(the reference raises a dtype mismatch inside F.linear)")
+        if self.device.type != "cuda":
+            raise RuntimeError("adafortitran_b200 has no CPU fallback: the model must live on a CUDA device")
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError("adafortitran_b200 is inference-only: call model.eval() or wrap the call in torch.no_grad()")
+        xin = x.to(device=self.device, dtype=torch.float32).reshape(x.size(0), self.linear.in_features).contiguous()
+        out = torch.empty((x.size(0), self.linear.out_features), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _capi.check(_capi.lib().aft_linear_forward(
+                C.c_void_p(self.linear.weight.data_ptr()), C.c_void_p(self.linear.bias.data_ptr()), C.c_void_p(xin.data_ptr()),
+                C.c_void_p(out.data_ptr()), x.size(0), self.linear.in_features, self.linear.out_features, C.c_void_p(stream)))
+        return out.reshape(-1, self.ofdm_size[0], self.ofdm_size[1])
+
+    def __repr__(self) -> str:
+        return f"LinearEstimator(\n  ofdm_size={self.ofdm_size},\n  pilot_size={self.pilot_size},\n  device={self.device}\n)"

@@ -137,6 +137,19 @@ AFT_API int aft_forward_host(AftHandle* h, const void* pilots, const float* snr,
  * sums[0] += sum|est-truth|^2, sums[1] += sum|truth|^2 over complex64 [count] arrays (device, fp64 sums). */
 AFT_API int aft_error_sums(const void* est, const void* truth, int64_t count, double* sums, void* stream);
 
+/* "Next" row N2: batched form of MatDataset._process_channel_data (reference src/data/dataset.py:95-144): the pilots
+ * of a sample are the non-zero entries of its sparse LS grid (complex64 [batch, cells], cells = subcarriers * symbols,
+ * row-major), in row-major order.  Writes the first `expected` of them to pilots[batch, expected] and the number of
+ * non-zero entries found to counts[batch] (int32, device); a count != expected is the reference's ValueError and is
+ * raised by the host binding.  All pointers are device pointers. */
+AFT_API int aft_extract_pilots(const void* ls_grid, void* pilots, int32_t* counts, int64_t batch, int32_t cells,
+                               int32_t expected, void* stream);
+
+/* "Next" row N3: LinearEstimator.forward (reference src/models/linear.py:60-95): y[batch, out_dim] =
+ * x[batch, in_dim] . W[out_dim, in_dim]^T + bias, fp32, device pointers. */
+AFT_API int aft_linear_forward(const float* weight, const float* bias, const float* x, float* y, int64_t batch,
+                               int32_t in_dim, int32_t out_dim, void* stream);
+
 /* Number of kernel launches issued by this library on the calling process since load (for bench.py). */
 AFT_API int64_t aft_launch_count(void);
 

@@ -307,3 +307,28 @@ def synthetic_channel(batch: int, snr_db: float, ds_ns: float, dop_hz: float, se
              + 1j * rng.standard_normal((batch, cfg.pilot_scs, cfg.pilot_symbols))) * sigma / math.sqrt(2)
     pilots = H[:, sc_idx][:, :, sym_idx] + noise
     return pilots.astype(np.complex64), H.astype(np.complex64)
+
+
+# --------------------------------------------------------------------------------------
+# "next" rows N2 / N3
+# --------------------------------------------------------------------------------------
+def extract_pilots(ls_grid: np.ndarray, pilot_size) -> np.ndarray:
+    """Reference ``MatDataset._process_channel_data`` (src/data/dataset.py:118-139), batched: the non-zero entries of
+    each sparse LS grid [B, scs, symbols] in row-major order, reshaped to [B, pilot_scs, pilot_symbols].
+    Raises ValueError when a sample does not hold exactly pilot_scs * pilot_symbols non-zero entries."""
+    ls_grid = np.asarray(ls_grid)
+    expected = int(pilot_size[0]) * int(pilot_size[1])
+    out = np.empty((ls_grid.shape[0], int(pilot_size[0]), int(pilot_size[1])), dtype=np.complex64)
+    for b in range(ls_grid.shape[0]):
+        flat = ls_grid[b].reshape(-1)
+        nz = flat[flat != 0]
+        if nz.size != expected:
+            raise ValueError(f"Expected {expected} pilot values, got {nz.size}")
+        out[b] = nz.reshape(out.shape[1:])
+    return out
+
+
+def linear_estimator(weight: np.ndarray, bias: np.ndarray, x: np.ndarray, ofdm_size) -> np.ndarray:
+    """Reference ``LinearEstimator.forward`` (src/models/linear.py:82-95): flatten, W x + b, reshape."""
+    y = x.reshape(x.shape[0], -1).astype(np.float64) @ weight.astype(np.float64).T + bias.astype(np.float64)
+    return y.reshape(-1, int(ofdm_size[0]), int(ofdm_size[1]))

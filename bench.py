@@ -248,7 +248,8 @@ def run_ours(args):
         _capi.check(lib.aft_error_sums(C.c_void_p(out.data_ptr()), C.c_void_p(truth.data_ptr()), out.numel(),
                                       C.c_void_p(sums.data_ptr()), C.c_void_p(st)))
         if world > 1:
-            del D.gather_estimates(out)[:0]        # NCCL warm-up at full size (communicator / buffer setup is not part of the path)
+            warm = D.gather_estimates(out)         # NCCL warm-up at full size (communicator / buffer setup is not part of the path)
+            del warm
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

@@ -61,6 +61,7 @@ using namespace ptx;
 #endif
 constexpr int kParts = AFT_TC_PARTS;   // threads per accumulator row = compute warpgroups (2: 8 warps x 224 regs, 4: 16 warps x 104 regs)
 static_assert(kParts == 2 || kParts == 4, "kParts must be 2 or 4");
+static_assert(kXImageBytes % (16 * 32 * 4 * kParts) == 0, "the copy-out of the result image assumes whole passes of the compute warps");
 constexpr int kComputeWarps = 4 * kParts;
 constexpr int kTcThreads = 32 * (kComputeWarps + 4);   // compute warpgroups + [idle, idle, producer, MMA]
 constexpr int kProducerWarp = kComputeWarps + 2, kMmaWarp = kComputeWarps + 3;   // highest warp ids: favoured by the issue arbiter
@@ -1285,13 +1286,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           if (t < 2 || tile2_active) {
             mbar_wait(misc + MB_F2_DONE + 8 * t, 1);
             tc_fence_after_sync();
-            epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, p.x_images, l == L - 1 ? seq : -1);
+            epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, nullptr, -1);
           }
           tc_fence_before_sync();
           fence_proxy_async_smem();
           warp_arrive(sb + OFF_BAR2 + MB2_X2_READY + 8 * t, lane);
         }
-        if (l == L - 1) warp_arrive(misc + MB_X_FREE, lane);
+        if (l == L - 1) {
+          // The encoder output replaces the sequence's input image in global memory: once every compute warp has written
+          // its LayerNorm2 rows, the X image is copied out with fully coalesced 16-byte accesses (512 B per warp
+          // instruction; storing from the LayerNorm registers would touch 32 different 128-byte lines per instruction).
+          named_bar_sync(10, 32 * kComputeWarps);
+          char* dst = p.x_images + seq * (int64_t)kXImageBytes;
+#pragma unroll
+          for (int i = 0; i < kXImageBytes / 16 / (32 * kComputeWarps); ++i) {
+            const uint32_t off = (uint32_t)(i * 32 * kComputeWarps + threadIdx.x) * 16;
+            *reinterpret_cast<uint4*>(dst + off) = ld_shared_v4(sb + OFF_X + off);
+          }
+          warp_arrive(misc + MB_X_FREE, lane);
+        }
         tl_event(p, tl, 341, tl_n);   // LayerNorm2 done
       }
     }

@@ -126,7 +126,10 @@ constexpr uint32_t kIdescPV = make_idesc_bf16(128, 32, false, true);     // B = 
 constexpr uint32_t kIdescN128 = make_idesc_bf16(128, 128, false, false);
 constexpr uint32_t kIdescN64 = make_idesc_bf16(128, 64, false, false);
 constexpr uint32_t kIdescST = make_idesc_bf16(128, 32, false, false);   // S^T block: A = 128 keys, B = 32 tail queries
-constexpr uint32_t kIdescOT = make_idesc_bf16(128, 32, true, true);     // O^T: A = V^T (MN-major), B = P^T (MN-major)
+#ifndef AFT_TC_OT_M
+#define AFT_TC_OT_M 64
+#endif
+constexpr uint32_t kIdescOT = make_idesc_bf16(AFT_TC_OT_M, 32, true, true);   // O^T: A = V^T (MN-major; only rows 0..31 = head dim matter), B = P^T (MN-major)
 // Tail tile exchange arrays ([4 quadrants][32 queries] f32 each): the padding rows 280..287 of the O image, chunk 0.
 // Those rows are never written during attention by the transposed path and out_proj only turns them into padding rows.
 constexpr uint32_t OFF_XT_MAX = OFF_O + 280 * 128, OFF_XT_SUM = OFF_XT_MAX + 512;
@@ -629,12 +632,17 @@ __device__ __forceinline__ void softmax_tail(uint32_t tmem, uint32_t sb, uint32_
   if (writer) st_shared_f32(sb + OFF_XT_SUM + xslot, sum[0]);
 }
 // O^T accumulator (lanes = head dim, columns = tail queries) -> / l -> bf16 -> O image rows 256..279 (quadrant 0 only)
-__device__ __forceinline__ void epi_o_tail(uint32_t tmem, uint32_t sb, int g, int obuf, int part, int lane) {
+// With M = 64 the accumulator rows sit in 16-lane groups: row d lives in lane 32 (d / 16) + d % 16, i.e. head-dim rows
+// 0..15 in quadrant 0 and 16..31 in quadrant 1 (lanes 0..15 each); with M = 128 row d is lane d (quadrant 0 only).
+constexpr int kOtQuads = AFT_TC_OT_M == 64 ? 2 : 1;
+__device__ __forceinline__ void epi_o_tail(uint32_t tmem, uint32_t sb, int g, int obuf, int q, int part, int lane) {
   uint32_t a[kTq];
-  tmem_ld_cols(tmem + TM_O + obuf * 32 + part * kTq, a);
+  tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_O + obuf * 32 + part * kTq, a);
   tmem_wait_ld();
-  const uint32_t colbyte = (uint32_t)(lane & 7) * 2;
-  const int u = (g & 1) * 4 + (lane >> 3);
+  if (AFT_TC_OT_M == 64 && lane >= 16) return;
+  const int d = AFT_TC_OT_M == 64 ? q * 16 + lane : lane;          // head-dim index of this thread's accumulator row
+  const uint32_t colbyte = (uint32_t)(d & 7) * 2;
+  const int u = (g & 1) * 4 + (d >> 3);
 #pragma unroll
   for (int v4 = 0; v4 < kTq / 4; ++v4) {
     float4 l4 = lds_f4(sb + OFF_XT_SUM + (part * kTq + v4 * 4) * 4);
@@ -1167,7 +1175,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             }
             if (t > 0) {
               if (t == 2) epi_o(tmem, sb, g, 1, (n_head + 1) & 1, inv_prev, q, part, lane);
-              else if (t == 3 && q == 0) epi_o_tail(tmem, sb, g, (n_head + 2) & 1, part, lane);
+              else if (t == 3 && q < kOtQuads) epi_o_tail(tmem, sb, g, (n_head + 2) & 1, q, part, lane);
               tc_fence_before_sync();
               fence_proxy_async_smem();
               warp_arrive(misc + MB_O_FREE + 8 * ((n_head + t - 1) & 1), lane);
@@ -1658,7 +1666,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_tail_kernel(const char
     warp_arrive(misc + MB_P_READY, lane);
     mbar_wait(misc + MB_PV_DONE, 0);
     tc_fence_after_sync();
-    if (q == 0) epi_o_tail(tmem, sb, 0, 1, part, lane);
+    if (q < kOtQuads) epi_o_tail(tmem, sb, 0, 1, q, part, lane);
     named_bar_sync(9, 32 * kComputeWarps);
     for (int i = threadIdx.x; i < 24 * 32; i += 32 * kComputeWarps) {
       const int r = 256 + i / 32, c = i % 32;

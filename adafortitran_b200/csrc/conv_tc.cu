@@ -164,7 +164,7 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   if ((sb & 1023u) != 0) __trap();
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar = sb + OFF_BAR;
   if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); fence_mbar_init(); }
   if (warp == 1) { tmem_alloc(bar + 16, 512); tmem_relinquish(); }

@@ -3,33 +3,38 @@
 //
 // One CTA per SM; a CTA owns one 280-token sequence at a time and carries it through all layers.  The
 // residual stream never leaves the SM: it lives in shared memory as the bf16 A-operand image of the next GEMM.
-// Per sequence the only HBM traffic is the 72 KB input image and the 140 KB fp32 result; weights (256 KB bf16
-// per layer) are streamed from L2 by 1-D bulk copies (cp.async.bulk) into a small ring.
+// Per sequence the only HBM traffic is the 72 KB input image and the 72 KB result image written over it; weights
+// (256 KB bf16 per layer) are streamed from L2 by 1-D bulk copies (cp.async.bulk) into a small ring.
 //
-//   warpgroup 2 : warp 10 = producer (bulk copies + expect_tx), warp 11 = MMA issuer (one thread issues every
-//                 tcgen05.mma, owns the TMEM allocation); warps 8,9 idle.  Registers shrunk with setmaxnreg.
-//   warpgroups 0,1 : 8 compute warps -- TMEM -> registers epilogues (bias, softmax, 1/l, residual + LayerNorm,
-//                 GELU), writing the next operand image (bf16) to shared memory / P to TMEM.  Registers grown
-//                 to 224 so a thread can hold a 144-wide score row or a 128-wide LayerNorm row.
+//   warps 0..15  : compute warps (4 warpgroups; warp w serves TMEM lane quadrant w % 4 = SM sub-partition w % 4, the four
+//                  warps of a quadrant split every accumulator row by columns) -- TMEM -> registers epilogues (bias,
+//                  softmax, 1/l, residual + LayerNorm, GELU), writing the next operand image (bf16) to shared memory /
+//                  P to TMEM.  setmaxnreg 104.
+//   warps 16..19 : control warpgroup (setmaxnreg 56): warp 18 = producer (bulk copies + expect_tx), warp 19 = MMA issuer
+//                  (the warp runs the schedule converged, the elected lane issues every tcgen05.mma / commit and owns
+//                  the TMEM allocation); warps 16, 17 idle.
 //
 // The MMA issuer and the compute warps each run a static program; they meet only through mbarriers
 // (tcgen05.commit -> "done" barriers; one arrive per compute warp -> "ready/free" barriers), so tensor-core work
 // for the next tile is in flight while the epilogue of the current one runs:  S(t+1) is issued as soon as S(t) is
-// in registers, P.V(t) runs under the exponentials of tile t+1, QKV(g+1) queues behind P.V of head g, FFN1 tiles
-// and FFN2 partial products are double buffered.
+// in registers, P.V(t) runs under the exponentials of tile t+1, the next head's projection is issued under the tail
+// tile, and the layer boundary is handed over per row tile (out_proj -> LayerNorm1 -> FFN1, FFN2 -> LayerNorm2 -> next
+// projection).  Protocol rules and the chaos build that tests them: DESIGN.md 4.1, tc_ptx.cuh (chaos_delay).
 //
-// All GEMMs use M = 128 row tiles (3 per sequence; the rows past 280 of the third tile read whatever follows in
-// shared memory -- rows of A are independent, the corresponding accumulator lanes are never read).
+// GEMMs use M = 128 row tiles (3 per sequence; the rows past 280 of the third tile read whatever follows in shared
+// memory -- rows of A are independent, the corresponding accumulator lanes are never read); the attention of the
+// 24-row tail tile runs transposed (see "tail tile" below).
 //
 // Shared memory map (bytes, every region 1024-aligned; operand layouts in tc_layout.cuh):
-//   O    [      0,  73728)  attention output image (A of out_proj)   | FFN: hidden chunk images, 2 x 36864
+//   O    [      0,  73728)  attention output image (A of out_proj)   | FFN: hidden images, 2 x 36864
+//                           (padding rows 280..287: tail-tile exchange arrays, second mbarrier block)
 //   X    [  73728, 147456)  residual stream image (A of QKV / FFN1, residual of both LayerNorms)
-//   QKV  [ 147456, 202752)  Q_g | K_g | V_g of the current head, 288 x 64 B each (SWIZZLE_64B)
-//                           | out_proj / FFN weight ring: 3 slots x 16384
-//   W    [ 202752, 227328)  in_proj slice of one head: rows q_g | k_g | v_g (96 x K=128)
-//   MISC [ 227328, 230400)  mbarriers, TMEM base, softmax max / sum exchange
+//   QKV  [ 147456, 202752)  Q_g | K_g | V_g of the current head, 288 x 64 B each (SWIZZLE_64B); P^T of the tail tile
+//                           | out_proj / FFN weight ring: 3 slots x 16384, then the layer's 4 KB vector block
+//   W    [ 202752, 227328)  in_proj slice of one head: rows q_g | k_g | v_g (96 x K=128) | FFN: second K-chunk of a W1 pair
+//   MISC [ 227328, 232448)  in_proj bias double buffer, mbarriers, TMEM base, softmax / LayerNorm exchange
 // Tensor memory map (columns): S [0,288)  P [288,432) (bf16 pairs)  O_acc x2 [432,464) [464,496);
-//   QKV accumulators alias S; out_proj / FFN2 accumulators [0,384); FFN1 accumulators [384,448) [448,512).
+//   QKV accumulators alias S; out_proj / FFN2 accumulators [0,384); one FFN1 accumulator tile [384,512).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -124,7 +129,6 @@ constexpr uint32_t kIdescQkv = make_idesc_bf16(128, 96, false, false);
 constexpr uint32_t kIdescS = make_idesc_bf16(128, 144, false, false);
 constexpr uint32_t kIdescPV = make_idesc_bf16(128, 32, false, true);     // B = V, MN-major
 constexpr uint32_t kIdescN128 = make_idesc_bf16(128, 128, false, false);
-constexpr uint32_t kIdescN64 = make_idesc_bf16(128, 64, false, false);
 constexpr uint32_t kIdescST = make_idesc_bf16(128, 32, false, false);   // S^T block: A = 128 keys, B = 32 tail queries
 #ifndef AFT_TC_OT_M
 #define AFT_TC_OT_M 64
@@ -186,17 +190,6 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float y = p * t * e;
   return fmaf(-ax, y, fmaxf(x, 0.f));
 }
-// GELU(x) = x Phi(x) with Phi(x) ~ 0.5 (1 + tanh(x (a + b x^2 + c x^4))), coefficients fitted to the erf form
-// (max |error| 2.5e-5 over the real line, plus the 2^-11 relative error of MUFU.TANH: |x| 2.4e-4 at most, i.e. at or
-// below the bf16 rounding of the hidden activations it feeds).  One MUFU and six FMA-pipe operations per element.
-__device__ __forceinline__ float gelu_tanh(float x) {
-  const float x2 = x * x;
-  const float u = x * fmaf(x2, fmaf(x2, -3.51516789e-4f, 3.70056460e-2f), 7.97507884e-1f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
 // Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): half the issue slots of the scalar forms, same rounding per lane.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
@@ -243,7 +236,9 @@ __device__ __forceinline__ uint32_t pack_bf16_pair(f32x2 v) {
   unpack2(v, lo, hi);
   return pack_bf16x2(lo, hi);
 }
-// gelu_tanh for a pair (packed arithmetic around the two MUFU.TANH)
+// GELU(x) = x Phi(x) with Phi(x) ~ 0.5 (1 + tanh(x (a + b x^2 + c x^4))), coefficients fitted to the erf form
+// (max |error| 2.5e-5 over the real line, plus the 2^-11 relative error of MUFU.TANH: |x| 2.4e-4 at most, i.e. at or
+// below the bf16 rounding of the hidden activations it feeds).  One MUFU per element; the arithmetic around it is packed fp32x2 (a pair of elements per call).
 __device__ __forceinline__ f32x2 gelu_tanh2(f32x2 x) {
   const f32x2 x2 = mul2(x, x);
   const f32x2 u = mul2(x, fma2(x2, fma2(x2, pack2(-3.51516789e-4f, -3.51516789e-4f), pack2(3.70056460e-2f, 3.70056460e-2f)),
@@ -254,10 +249,6 @@ __device__ __forceinline__ f32x2 gelu_tanh2(f32x2 x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(ub));
   const f32x2 hx = mul2(x, pack2(0.5f, 0.5f));
   return fma2(hx, pack2(ta, tb), hx);
-}
-__device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
-  lo = __uint_as_float(w << 16);
-  hi = __uint_as_float(w & 0xFFFF0000u);
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
@@ -273,12 +264,6 @@ __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-// 16-byte load from the constant bank that the compiler may not hoist (keeps the epilogues' live ranges short)
-__device__ __forceinline__ float4 ldc_v4(const float* p) {
-  float4 v;
-  asm volatile("ld.const.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(__cvta_generic_to_constant(p)));
   return v;
 }
 template <int N>

@@ -187,3 +187,61 @@ def test_collate_on_device(tmp_path):
     with torch.no_grad():
         y = m(pilots, meta)
     assert tuple(y.shape) == (4, 120, 14) and bool(torch.isfinite(torch.view_as_real(y)).all())
+
+
+# ----------------------------------------------------------------------------------------- N4: evaluator
+def _write_test_sets(root, names_by_dir, seed=21):
+    import scipy.io as sio
+    rng = np.random.default_rng(seed)
+    for sub, names in names_by_dir.items():
+        (root / sub).mkdir(parents=True)
+        for n in names:
+            H = np.zeros((120, 14, 3), dtype=np.complex64)
+            H[:, :, 0] = (rng.standard_normal((120, 14)) + 1j * rng.standard_normal((120, 14))).astype(np.complex64) * 0.7
+            ls = np.zeros((120, 14), dtype=np.complex64)
+            ls[0:120:10, [2, 11]] = H[0:120:10, :, 0][:, [2, 11]] + 0.05 * (rng.standard_normal((12, 2)) + 1j * rng.standard_normal((12, 2)))
+            H[:, :, 1] = ls
+            sio.savemat(root / sub / n, {"H": H})
+
+
+@pytest.mark.gpu
+def test_evaluator_matches_reference_formula(tmp_path):
+    """Folder sweep through the B200 ModelEvaluator vs the reference formula evaluated with the CPU port of the model:
+    sum_b 2 * MSELoss(cat(re, im)) * B_b / sum_b B_b, to_db (trainer.py:328-347)."""
+    from adafortitran_b200 import evaluate
+    from adafortitran_b200.config import PilotParams
+    from oracle.torch_port import TorchPort
+    sets = {"DS_50": [f"{i}_SNR-20_DS-50_DOP-500_N-3_TDL-A.mat" for i in range(1, 8)],
+            "DS_200": [f"{i}_SNR-10_DS-200_DOP-900_N-3_TDL-B.mat" for i in range(1, 6)]}
+    _write_test_sets(tmp_path, sets)
+    sd = util.ada_weights()
+    model = util.make_model("ada", weights=sd, precision="fp32")
+    loaders = evaluate.get_test_dataloaders(tmp_path, PilotParams(num_scs=12, num_symbols=2), batch_size=3)
+    assert sorted(n for n, _ in loaders) == ["DS_200", "DS_50"]
+    stats = evaluate.ModelEvaluator(model, model.device).get_test_stats(loaders)
+    assert list(stats) == [50, 200]
+    # reference side: CPU port of the model + the reference's metric, batch by batch
+    port = TorchPort(sd, adaptive=True).eval()
+    for sub, names in sets.items():
+        ds = data.MatDataset(tmp_path / sub, (12, 2))
+        total, n = 0.0, 0
+        for i0 in range(0, len(ds), 3):
+            items = [ds[i] for i in range(i0, min(i0 + 3, len(ds)))]
+            x = torch.stack([it[0] for it in items]); h = torch.stack([it[1] for it in items])
+            meta = [torch.stack([it[2][k] for it in items]) for k in range(5)]
+            with torch.no_grad():
+                y = port(x, meta[1].reshape(-1), meta[2].reshape(-1), meta[3].reshape(-1))
+            cat = lambda t: torch.cat((t.real, t.imag), dim=1)
+            loss = torch.nn.functional.mse_loss(cat(y), cat(h))
+            total += 2 * loss.item() * len(items); n += len(items)
+        want = 10 * np.log10(total / n)
+        assert abs(stats[int(sub.split("_")[1])] - want) <= 2e-3, (sub, stats, want)
+    # checkpoint in the reference's format
+    ck = tmp_path / "checkpoint_epoch_3.pt"
+    torch.save({"epoch": 3, "model_state_dict": util.to_torch(sd)}, ck)
+    fresh = util.make_model("ada", precision="fp32")
+    assert evaluate.load_checkpoint(fresh, ck) == 3
+    again = evaluate.ModelEvaluator(fresh, fresh.device).get_test_stats(evaluate.get_test_dataloaders(tmp_path, PilotParams(num_scs=12, num_symbols=2), 4))
+    assert all(abs(again[k] - stats[k]) <= 1e-6 for k in stats)
+    chans = evaluate.ModelEvaluator(fresh, fresh.device).predict_channels(loaders)
+    assert sorted(chans) == [50, 200] and tuple(chans[50]["estimated_channel"].shape) == (120, 14)

@@ -88,6 +88,11 @@ using namespace aft;
 // ---------------------------------------------------------------------------------------------
 struct AftHandle {
   AftConfig cfg;
+  // Shape mode.  false: the reference default grid, served by the specialised kernels (both precisions).  true: any
+  // other grid / pilot / patch geometry, served by the shape-generic AFT_FP32 kernels (generic_f32.cu); AFT_BF16 is
+  // rejected for such a handle.
+  bool generic = false;
+  int H = kGridH, W = kGridW, P = kPilots, ph = kPatchH, pw = kPatchW, S = kS, pix = kPix, patch_len = kPatchLen;
   int device = -1;
   int sm_count = 0;
   bool loaded = false;
@@ -131,24 +136,31 @@ size_t ws_bytes_f32(int64_t bc) {
   return f * sizeof(float);
 }
 
-int validate(const AftConfig& c) {
+int validate(const AftConfig& c, bool* generic) {
   auto bad = [](const char* what) {
-    set_error("unsupported configuration: %s (kernels are specialised for the reference default shape: grid 120x14, "
-              "pilots 12x2, patch 3x2, model_dim 128, 4 heads, ff 256, adapter [h1<=64, h2<=64, 560])", what);
+    set_error("unsupported configuration: %s (supported: model_dim 128, 4 heads, ff 256, adapter [h1<=64, h2<=64, 2*tokens], "
+              "patch sizes dividing the grid; the tensor-core AFT_BF16 path additionally needs the reference default grid "
+              "120x14, pilots 12x2, patch 3x2)", what);
     return AFT_ERR_UNSUPPORTED;
   };
-  if (c.num_scs != kGridH || c.num_symbols != kGridW) return bad("ofdm grid");
-  if (c.pilot_scs * c.pilot_symbols != kPilots || c.pilot_scs != 12) return bad("pilot grid");
-  if (c.patch_scs != kPatchH || c.patch_symbols != kPatchW) return bad("patch_size");
   if (c.model_dim != kD || c.num_head != kH || c.ff_dim != kFF) return bad("model_dim / num_head / ff_dim");
   if (c.num_layers < 1 || c.num_layers > kMaxLayers) return bad("num_layers");
   if (c.activation != AFT_ACT_RELU && c.activation != AFT_ACT_GELU) return bad("activation");
-  if (c.max_seq_len < kS) return bad("max_seq_len < sequence length");
+  if (c.num_scs < 1 || c.num_symbols < 1 || c.pilot_scs < 1 || c.pilot_symbols < 1) return bad("grid extents");
+  if (c.patch_scs < 1 || c.patch_symbols < 1 || c.num_scs % c.patch_scs != 0 || c.num_symbols % c.patch_symbols != 0)
+    return bad("patch_size must divide the ofdm grid");
+  if (c.patch_scs * c.patch_symbols > 64) return bad("patch_size (more than 64 elements)");
+  if ((int64_t)c.pilot_scs * c.pilot_symbols > 4096) return bad("more than 4096 pilots");
+  if ((int64_t)c.num_scs * c.num_symbols > (1 << 22)) return bad("ofdm grid (more than 4M points)");
+  const int S = (c.num_scs / c.patch_scs) * (c.num_symbols / c.patch_symbols);
+  if (c.max_seq_len < S) return bad("max_seq_len < sequence length");
   if (c.adaptive) {
     if (c.adapt_h1 < 1 || c.adapt_h1 > kMaxAdaHidden || c.adapt_h2 < 1 || c.adapt_h2 > kMaxAdaHidden) return bad("adapter hidden sizes");
-    if (c.adapt_h3 != 2 * kS) return bad("channel_adaptivity_hidden_sizes[2] must be 2*num_patches");
+    if (c.adapt_h3 != 2 * S) return bad("channel_adaptivity_hidden_sizes[2] must be 2*num_patches");
     if (c.adaptive_token_length != kAda) return bad("adaptive_token_length");
   }
+  *generic = !(c.num_scs == kGridH && c.num_symbols == kGridW && c.pilot_scs == 12 && c.pilot_symbols == 2 &&
+               c.patch_scs == kPatchH && c.patch_symbols == kPatchW);
   return AFT_OK;
 }
 
@@ -170,27 +182,27 @@ size_t layout_arena(AftHandle* h, float* base) {
     p.w0 = a.take(72); p.w1 = a.take(2304); p.w2 = a.take(2304); p.w3 = a.take(72);
     p.b0 = a.take(8); p.b1 = a.take(32); p.b2 = a.take(8); p.b3 = a.take(8);
   };
-  const int in_dim = kPatchLen + (c.adaptive ? kAda : 0);
-  h->front.up_wt = a.take(kPilots * kPix);
-  h->front.up_b = a.take(kPix);
+  const int in_dim = h->patch_len + (c.adaptive ? kAda : 0);
+  h->front.up_wt = a.take((size_t)h->P * h->pix);
+  h->front.up_b = a.take(h->pix);
   conv(h->front.enh);
   for (int m = 0; m < 3; ++m) {
     MlpPack& mp = h->front.mlp[m];
     if (c.adaptive) {
       mp.w0 = a.take(c.adapt_h1); mp.b0 = a.take(c.adapt_h1);
       mp.w1 = a.take((size_t)c.adapt_h2 * c.adapt_h1); mp.b1 = a.take(c.adapt_h2);
-      mp.w2t = a.take((size_t)c.adapt_h2 * 2 * kS); mp.b2 = a.take(2 * kS);
+      mp.w2t = a.take((size_t)c.adapt_h2 * 2 * h->S); mp.b2 = a.take(2 * h->S);
     } else {
       mp = MlpPack{};
     }
   }
   h->front.h1 = c.adapt_h1; h->front.h2 = c.adapt_h2;
   h->front.l1_wt = a.take((size_t)in_dim * kD);
-  h->front.posb = a.take((size_t)kS * kD);
+  h->front.posb = a.take((size_t)h->S * kD);
   h->front.in_dim = in_dim;
   h->front.adaptive = c.adaptive;
-  h->head.l2_w = a.take(kPatchLen * kD);
-  h->head.l2_b = a.take(8);
+  h->head.l2_w = a.take((size_t)h->patch_len * kD);
+  h->head.l2_b = a.take(64);
   conv(h->head.refine);
   h->layers.resize(c.num_layers);
   for (auto& L : h->layers) {
@@ -263,7 +275,57 @@ int forward_chunk_f32(AftHandle* h, const float2* pilots, const float* snr, cons
   return AFT_OK;
 }
 
-int64_t chunk_for(int precision) { return precision == AFT_BF16 ? kChunkBf16 : kChunkF32; }
+// ---- shape-generic AFT_FP32 path (generic_f32.cu)
+size_t generic_floats_per_chunk(const AftHandle* h, int64_t bc) {
+  const size_t nseq = 2 * (size_t)bc, M = nseq * h->S;
+  size_t f = 0;
+  f += align_up(nseq * h->pix, 64);          // enh
+  f += align_up(M * kD, 64);                 // h
+  f += align_up(M * 3 * kD, 64);             // qkv (ffn hidden aliases it)
+  f += align_up(M * kD, 64);                 // attention output
+  const size_t a = generic_front_scratch_floats(bc, h->P, h->pix, h->S), b = generic_head_scratch_floats(bc, h->pix);
+  f += align_up(a > b ? a : b, 64);          // frontend / head scratch (conv planes)
+  return f;
+}
+// samples per internal chunk: about 1 GB of scratch, at least one sample
+int64_t generic_chunk(const AftHandle* h) {
+  const size_t per = generic_floats_per_chunk(h, 1) * sizeof(float);
+  int64_t bc = (int64_t)((size_t(1) << 30) / (per ? per : 1));
+  if (bc < 1) bc = 1;
+  if (bc > kChunkF32) bc = kChunkF32;
+  return bc;
+}
+
+int forward_chunk_generic(AftHandle* h, const float2* pilots, const float* snr, const float* ds, const float* dop, float2* out,
+                          int64_t bc, float* ws, cudaStream_t st) {
+  const int64_t nseq = 2 * bc, M = nseq * h->S;
+  float* enh = ws;
+  float* hbuf = enh + align_up((size_t)nseq * h->pix, 64);
+  float* qkv = hbuf + align_up((size_t)M * kD, 64);
+  float* att = qkv + align_up((size_t)M * 3 * kD, 64);
+  float* scratch = att + align_up((size_t)M * kD, 64);
+  float* ffn = qkv;
+  prof_mark(h, st);
+  if (!launch_generic_frontend(h->front, pilots, snr, ds, dop, enh, hbuf, scratch, bc, h->H, h->W, h->P, h->ph, h->pw, st)) return AFT_ERR_CUDA;
+  prof_mark(h, st);
+  for (const LayerPackF32& L : h->layers) {
+    if (!launch_gemm_f32(kEpiBias, hbuf, L.in_w, L.in_b, qkv, M, 3 * kD, kD, 0, nullptr, nullptr, nullptr, st)) return AFT_ERR_CUDA;
+    if (!launch_generic_attention(qkv, att, nseq, h->S, st)) return AFT_ERR_CUDA;
+    if (!launch_gemm_f32(kEpiBiasResLn, att, L.out_w, L.out_b, hbuf, M, kD, kD, 0, hbuf, L.n1_w, L.n1_b, st)) return AFT_ERR_CUDA;
+    if (!launch_gemm_f32(kEpiBiasAct, hbuf, L.l1_w, L.l1_b, ffn, M, kFF, kD, h->cfg.activation, nullptr, nullptr, nullptr, st)) return AFT_ERR_CUDA;
+    if (!launch_gemm_f32(kEpiBiasResLn, ffn, L.l2_w, L.l2_b, hbuf, M, kD, kFF, 0, hbuf, L.n2_w, L.n2_b, st)) return AFT_ERR_CUDA;
+  }
+  prof_mark(h, st);
+  if (!launch_generic_head(h->head, hbuf, enh, out, scratch, bc, h->H, h->W, h->ph, h->pw, st)) return AFT_ERR_CUDA;
+  prof_mark(h, st);
+  if (h->profile) { h->prof_launches[0] += 1; h->prof_launches[1] += 5 * (int64_t)h->layers.size(); h->prof_launches[2] += 1; }
+  return AFT_OK;
+}
+
+int64_t chunk_for(const AftHandle* h, int precision) {
+  if (h->generic) return generic_chunk(h);
+  return precision == AFT_BF16 ? kChunkBf16 : kChunkF32;
+}
 
 }  // namespace
 
@@ -281,7 +343,8 @@ int64_t aft_launch_count(void) { return g_launches.load(std::memory_order_relaxe
 int aft_create(const AftConfig* cfg, AftHandle** out) {
   if (!cfg || !out) { set_error("aft_create: NULL argument"); return AFT_ERR_INVALID; }
   *out = nullptr;
-  const int v = validate(*cfg);
+  bool generic = false;
+  const int v = validate(*cfg, &generic);
   if (v != AFT_OK) return v;
   int dev = -1;
   AFT_CUDA(cudaGetDevice(&dev));
@@ -295,6 +358,10 @@ int aft_create(const AftConfig* cfg, AftHandle** out) {
   AftHandle* h = new (std::nothrow) AftHandle();
   if (!h) { set_error("aft_create: out of host memory"); return AFT_ERR_INVALID; }
   h->cfg = *cfg;
+  h->generic = generic;
+  h->H = cfg->num_scs; h->W = cfg->num_symbols; h->P = cfg->pilot_scs * cfg->pilot_symbols;
+  h->ph = cfg->patch_scs; h->pw = cfg->patch_symbols; h->patch_len = h->ph * h->pw;
+  h->S = (h->H / h->ph) * (h->W / h->pw); h->pix = h->H * h->W;
   h->device = dev;
   h->sm_count = prop.multiProcessorCount;
   h->arena_floats = layout_arena(h, nullptr);
@@ -341,9 +408,16 @@ int aft_load_weights(AftHandle* h, const AftWeights* w, void* stream) {
     return AFT_ERR_INVALID;
   }
   auto mut = [](const float* p) { return const_cast<float*>(p); };
-  k_transpose<<<blocks_for(kPix * kPilots), 256, 0, st>>>(w->upsampler_w, mut(h->front.up_wt), kPix, kPilots);
-  count_launch();
-  if (!copy_to(w->upsampler_b, h->front.up_b, kPix, st, "pilot_upsampler.bias")) return AFT_ERR_CUDA;
+  if (h->generic) {   // the generic linear kernel reads W [out][in] as it is
+    if (cudaMemcpyAsync(mut(h->front.up_wt), w->upsampler_w, (size_t)h->pix * h->P * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("aft_load_weights: copy of pilot_upsampler.weight failed");
+      return AFT_ERR_CUDA;
+    }
+  } else {
+    k_transpose<<<blocks_for(kPix * kPilots), 256, 0, st>>>(w->upsampler_w, mut(h->front.up_wt), kPix, kPilots);
+    count_launch();
+  }
+  if (!copy_to(w->upsampler_b, h->front.up_b, h->pix, st, "pilot_upsampler.bias")) return AFT_ERR_CUDA;
   if (!pack_conv(w->initial_enhancer, h->front.enh, st)) return AFT_ERR_CUDA;
   if (!pack_conv(w->final_refiner, h->head.refine, st)) return AFT_ERR_CUDA;
   if (c.adaptive) {
@@ -356,16 +430,16 @@ int aft_load_weights(AftHandle* h, const AftWeights* w, void* stream) {
       if (!copy_to(src[m]->b[0], mp.b0, c.adapt_h1, st, "adapter.0.bias")) return AFT_ERR_CUDA;
       if (!copy_to(src[m]->w[1], mp.w1, c.adapt_h2 * c.adapt_h1, st, "adapter.2.weight")) return AFT_ERR_CUDA;
       if (!copy_to(src[m]->b[1], mp.b1, c.adapt_h2, st, "adapter.2.bias")) return AFT_ERR_CUDA;
-      k_transpose<<<blocks_for(2 * kS * c.adapt_h2), 256, 0, st>>>(src[m]->w[2], mut(mp.w2t), 2 * kS, c.adapt_h2);
+      k_transpose<<<blocks_for(2 * h->S * c.adapt_h2), 256, 0, st>>>(src[m]->w[2], mut(mp.w2t), 2 * h->S, c.adapt_h2);
       count_launch();
-      if (!copy_to(src[m]->b[2], mp.b2, 2 * kS, st, "adapter.4.bias")) return AFT_ERR_CUDA;
+      if (!copy_to(src[m]->b[2], mp.b2, 2 * h->S, st, "adapter.4.bias")) return AFT_ERR_CUDA;
     }
   }
   k_transpose<<<blocks_for(kD * h->front.in_dim), 256, 0, st>>>(w->linear_1_w, mut(h->front.l1_wt), kD, h->front.in_dim);
-  k_posb<<<blocks_for(kS * kD), 256, 0, st>>>(w->pos_table, w->linear_1_b, mut(h->front.posb), kS * kD, kD);
+  k_posb<<<blocks_for(h->S * kD), 256, 0, st>>>(w->pos_table, w->linear_1_b, mut(h->front.posb), h->S * kD, kD);
   count_launch(2);
-  if (!copy_to(w->linear_2_w, h->head.l2_w, kPatchLen * kD, st, "linear_2.weight")) return AFT_ERR_CUDA;
-  if (!copy_to(w->linear_2_b, h->head.l2_b, kPatchLen, st, "linear_2.bias")) return AFT_ERR_CUDA;
+  if (!copy_to(w->linear_2_w, h->head.l2_w, h->patch_len * kD, st, "linear_2.weight")) return AFT_ERR_CUDA;
+  if (!copy_to(w->linear_2_b, h->head.l2_b, h->patch_len, st, "linear_2.bias")) return AFT_ERR_CUDA;
   for (int l = 0; l < c.num_layers; ++l) {
     const AftEncoderLayer& s = w->layers[l];
     const LayerPackF32& d = h->layers[l];
@@ -379,7 +453,7 @@ int aft_load_weights(AftHandle* h, const AftWeights* w, void* stream) {
     for (const auto& it : items)
       if (!copy_to(it.s, it.d, it.n, st, it.name)) return AFT_ERR_CUDA;
   }
-  if (!tc_weights_pack(h->tc, h->layers, h->front.enh, h->head.refine, st)) return AFT_ERR_CUDA;
+  if (!h->generic && !tc_weights_pack(h->tc, h->layers, h->front.enh, h->head.refine, st)) return AFT_ERR_CUDA;
   if (!check_launch("aft_load_weights")) return AFT_ERR_CUDA;
   h->loaded = true;
   return AFT_OK;
@@ -388,8 +462,9 @@ int aft_load_weights(AftHandle* h, const AftWeights* w, void* stream) {
 size_t aft_workspace_bytes(const AftHandle* h, int64_t batch, int precision) {
   if (!h || batch < 0) { set_error("aft_workspace_bytes: bad argument"); return 0; }
   if (precision != AFT_FP32 && precision != AFT_BF16) { set_error("aft_workspace_bytes: bad precision"); return 0; }
-  int64_t bc = batch < chunk_for(precision) ? batch : chunk_for(precision);
+  int64_t bc = batch < chunk_for(h, precision) ? batch : chunk_for(h, precision);
   if (bc < 1) bc = 1;
+  if (h->generic) return generic_floats_per_chunk(h, bc) * sizeof(float);
   return precision == AFT_BF16 ? tc_workspace_bytes(bc) : ws_bytes_f32(bc);
 }
 
@@ -399,6 +474,11 @@ int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float*
   if (batch < 0) { set_error("aft_forward: negative batch"); return AFT_ERR_INVALID; }
   if (precision != AFT_FP32 && precision != AFT_BF16) { set_error("aft_forward: bad precision %d", precision); return AFT_ERR_INVALID; }
   if (!h->loaded) { set_error("aft_forward: weights not loaded (call aft_load_weights first)"); return AFT_ERR_STATE; }
+  if (h->generic && precision == AFT_BF16) {
+    set_error("aft_forward: the tensor-core AFT_BF16 path is specialised for the reference default grid (120x14, pilots 12x2, "
+              "patch 3x2); this %dx%d model runs with AFT_FP32 only", h->H, h->W);
+    return AFT_ERR_UNSUPPORTED;
+  }
   if (batch == 0) return AFT_OK;
   if (!pilots || !out) { set_error("aft_forward: NULL pilots / out"); return AFT_ERR_INVALID; }
   if (h->cfg.adaptive) {
@@ -417,7 +497,7 @@ int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float*
     return AFT_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t chunk = chunk_for(precision);
+  const int64_t chunk = chunk_for(h, precision);
   const float2* pin = static_cast<const float2*>(pilots);
   float2* pout = static_cast<float2*>(out);
   for (int64_t c0 = 0; c0 < batch; c0 += chunk) {
@@ -426,7 +506,9 @@ int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float*
     const float* s1 = h->cfg.adaptive ? delay_spread + c0 : nullptr;
     const float* s2 = h->cfg.adaptive ? doppler + c0 : nullptr;
     int rc;
-    if (precision == AFT_FP32) {
+    if (h->generic) {
+      rc = forward_chunk_generic(h, pin + c0 * h->P, s0, s1, s2, pout + c0 * h->pix, bc, static_cast<float*>(workspace), st);
+    } else if (precision == AFT_FP32) {
       rc = forward_chunk_f32(h, pin + c0 * kPilots, s0, s1, s2, pout + c0 * kPix, bc, static_cast<float*>(workspace), st);
     } else {
       TcProfileHook hook{h->profile ? &prof_mark_cb : nullptr, h};
@@ -450,9 +532,10 @@ int aft_forward_host(AftHandle* h, const void* pilots, const float* snr, const f
     set_error("aft_forward_host: meta_data is required when channel adaptation is enabled");
     return AFT_ERR_INVALID;
   }
-  const int64_t hc = batch < kHostChunk ? batch : kHostChunk;
-  const size_t in_bytes = (size_t)hc * (kPilots * sizeof(float2) + 3 * sizeof(float));
-  const size_t out_bytes = (size_t)hc * kPix * sizeof(float2);
+  int64_t hc = batch < kHostChunk ? batch : kHostChunk;
+  if (h->generic && hc > chunk_for(h, precision)) hc = chunk_for(h, precision);
+  const size_t in_bytes = (size_t)hc * (h->P * sizeof(float2) + 3 * sizeof(float));
+  const size_t out_bytes = (size_t)hc * h->pix * sizeof(float2);
   const size_t ws_need = aft_workspace_bytes(h, hc, precision);
   if (ws_need == 0) return AFT_ERR_INVALID;
   for (auto& ln : h->lanes) {
@@ -479,8 +562,8 @@ int aft_forward_host(AftHandle* h, const void* pilots, const float* snr, const f
     AftHandle::HostLane& ln = h->lanes[lane];
     const int64_t bc = batch - c0 < hc ? batch - c0 : hc;
     char* din = static_cast<char*>(ln.d_in);
-    float* dmeta = reinterpret_cast<float*>(din + (size_t)ln.cap * kPilots * sizeof(float2));
-    AFT_CUDA(cudaMemcpyAsync(din, hp + (size_t)c0 * kPilots * sizeof(float2), (size_t)bc * kPilots * sizeof(float2),
+    float* dmeta = reinterpret_cast<float*>(din + (size_t)ln.cap * h->P * sizeof(float2));
+    AFT_CUDA(cudaMemcpyAsync(din, hp + (size_t)c0 * h->P * sizeof(float2), (size_t)bc * h->P * sizeof(float2),
                              cudaMemcpyHostToDevice, ln.stream));
     if (ada) {
       AFT_CUDA(cudaMemcpyAsync(dmeta, snr + c0, bc * sizeof(float), cudaMemcpyHostToDevice, ln.stream));
@@ -490,7 +573,7 @@ int aft_forward_host(AftHandle* h, const void* pilots, const float* snr, const f
     const int rc = aft_forward(h, din, ada ? dmeta : nullptr, ada ? dmeta + ln.cap : nullptr, ada ? dmeta + 2 * ln.cap : nullptr,
                                ln.d_out, bc, precision, ln.ws, ln.ws_bytes, ln.stream);
     if (rc != AFT_OK) return rc;
-    AFT_CUDA(cudaMemcpyAsync(ho + (size_t)c0 * kPix * sizeof(float2), ln.d_out, (size_t)bc * kPix * sizeof(float2),
+    AFT_CUDA(cudaMemcpyAsync(ho + (size_t)c0 * h->pix * sizeof(float2), ln.d_out, (size_t)bc * h->pix * sizeof(float2),
                              cudaMemcpyDeviceToHost, ln.stream));
   }
   AFT_CUDA(cudaStreamSynchronize(h->lanes[0].stream));

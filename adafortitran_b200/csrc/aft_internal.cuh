@@ -121,6 +121,15 @@ bool launch_attn_f32(const float* qkv, float* out, int64_t nseq, cudaStream_t st
 bool launch_extract_pilots(const float2* grid, float2* pilots, int32_t* counts, int64_t batch, int cells, int expected, cudaStream_t st);
 bool launch_linear(const float* w, const float* bias, const float* x, float* y, int64_t batch, int in_dim, int out_dim, cudaStream_t st);
 
+// generic_f32.cu : AFT_FP32 path for non-default grids (activations in global memory, runtime extents)
+size_t generic_front_scratch_floats(int64_t nsamples, int P, int pix, int S);
+size_t generic_head_scratch_floats(int64_t nsamples, int pix);
+bool launch_generic_frontend(const FrontPack& p, const float2* pilots, const float* snr, const float* ds, const float* dop, float* enh,
+                             float* h, float* scratch, int64_t nsamples, int H, int W, int P, int ph, int pw, cudaStream_t st);
+bool launch_generic_attention(const float* qkv, float* out, int64_t nseq, int S, cudaStream_t st);
+bool launch_generic_head(const HeadPack& p, const float* h, const float* enh, float2* out, float* scratch, int64_t nsamples, int H, int W,
+                         int ph, int pw, cudaStream_t st);
+
 // reduce.cu
 bool launch_error_sums(const float2* est, const float2* truth, int64_t count, double* sums, cudaStream_t st);
 

@@ -178,6 +178,12 @@ bool launch_linear(const float* w, const float* bias, const float* x, float* y, 
     }
     linear_kernel<true><<<(unsigned)blocks, 256, wbytes + xbytes, st>>>(w, bias, x, y, batch, in_dim, out_dim);
   } else {
+    if (xbytes > 48 * 1024 &&
+        cudaFuncSetAttribute(linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xbytes) != cudaSuccess) {
+      set_error("linear_kernel: cannot opt in to %zu bytes of shared memory", xbytes);
+      return false;
+    }
+    if (blocks < 148 && out_dim > 4096) blocks = 148;   // few samples, many outputs: idle CTAs cost nothing
     linear_kernel<false><<<(unsigned)blocks, 256, xbytes, st>>>(w, bias, x, y, batch, in_dim, out_dim);
   }
   count_launch();

@@ -103,7 +103,10 @@ AFT_API const char* aft_last_error(void);
 
 /* Replaces the constructor BaseFortiTranEstimator.__init__ / _setup_dimensions / _build_architecture
  * (reference src/models/fortitran.py:23-126).  Validates the shape against what the kernels support and
- * allocates the packed-weight arena on the current device. */
+ * allocates the packed-weight arena on the current device.  Supported: model_dim 128, 4 heads, ff 256, patch sizes
+ * dividing the grid.  The reference default geometry (grid 120x14, pilots 12x2, patch 3x2) runs in both precisions;
+ * any other geometry runs with AFT_FP32 only (shape-generic kernels) and aft_forward rejects AFT_BF16 for it
+ * with AFT_ERR_UNSUPPORTED. */
 AFT_API int aft_create(const AftConfig* cfg, AftHandle** out);
 AFT_API void aft_destroy(AftHandle* h);
 

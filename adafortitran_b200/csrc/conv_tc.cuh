@@ -50,6 +50,9 @@ constexpr int kStackSmemBytes = OFF_BAR + 256;          // 230,272
 // group; the fp32 result and the callers' scratch live there (behind the 512-byte front guard, which must stay zero).
 constexpr int OFF_OUT = OFF_MID + kPosGuard * 16;                   // fp32 result, unpadded [1680]
 constexpr int OFF_SCRATCH = OFF_MID + kPlaneBytes + kPosGuard * 16; // 32,768 bytes of caller scratch (group 1)
+// The second a1 group is no longer an MMA operand (conv2 packs two taps into K instead of 8 channels + 8 zero channels):
+// 33,792 bytes that stack_run never touches -- persistent caller scratch.
+constexpr int OFF_KEEP = OFF_A1 + kPlaneBytes;
 
 __device__ __forceinline__ uint64_t desc_k_none(uint32_t saddr, uint32_t lbo_bytes) {
   return make_smem_desc(saddr, lbo_bytes, 128, kSwizzleNone);   // SBO = 128: next 8 rows (positions / couts)

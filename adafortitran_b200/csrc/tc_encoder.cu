@@ -511,10 +511,9 @@ __device__ __forceinline__ void epi_o_store(uint32_t sb, int g, int t, float inv
 #pragma unroll
   for (int i = 0; i < kOCols / 8; ++i) {
     const int u = (g & 1) * 4 + part * (kOCols / 8) + i;
-    st_shared_v4(row + ((u ^ (r & 7)) << 4), pack_bf16x2(__uint_as_float(a[8 * i]) * inv_l, __uint_as_float(a[8 * i + 1]) * inv_l),
-                 pack_bf16x2(__uint_as_float(a[8 * i + 2]) * inv_l, __uint_as_float(a[8 * i + 3]) * inv_l),
-                 pack_bf16x2(__uint_as_float(a[8 * i + 4]) * inv_l, __uint_as_float(a[8 * i + 5]) * inv_l),
-                 pack_bf16x2(__uint_as_float(a[8 * i + 6]) * inv_l, __uint_as_float(a[8 * i + 7]) * inv_l));
+    const f32x2 il = pack2(inv_l, inv_l);
+    auto sc = [&](int j) { return pack_bf16_pair(mul2(pack2(__uint_as_float(a[8 * i + j]), __uint_as_float(a[8 * i + j + 1])), il)); };
+    st_shared_v4(row + ((u ^ (r & 7)) << 4), sc(0), sc(2), sc(4), sc(6));
   }
 }
 
@@ -589,16 +588,30 @@ __device__ __forceinline__ void softmax_tail(uint32_t tmem, uint32_t sb, uint32_
       const float4 o = lds_f4(sb + OFF_XT_MAX + (qq * 32 + part * kTq + u * 4) * 4);
       m4.x = fmaxf(m4.x, o.x); m4.y = fmaxf(m4.y, o.y); m4.z = fmaxf(m4.z, o.z); m4.w = fmaxf(m4.w, o.w);
     }
-    const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+    // pairs of query columns; key block 1 goes through the FMA-pipe polynomial (one exponential in three, as in the
+    // full tiles), blocks 0 and 2 through the MUFU
+    const f32x2 nm[2] = {pack2(-m4.x, -m4.y), pack2(-m4.z, -m4.w)};
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = u * 4 + jj;
-      float acc = 0.f;
+    for (int jp = 0; jp < 2; ++jp) {
+      const int j = u * 4 + 2 * jp;
+      f32x2 acc = pack2(0.f, 0.f);
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        if (b < nb) { s[b][j] = ex2(s[b][j] - mm[jj]); acc += s[b][j]; }
+        if (b < nb) {
+          const f32x2 x2 = add2(pack2(s[b][j], s[b][j + 1]), nm[jp]);
+          f32x2 e2;
+          if (AFT_TC_POLY_EXP > 0 && b == 1) {
+            e2 = ex2_poly2(x2);
+          } else {
+            float a, c;
+            unpack2(x2, a, c);
+            e2 = pack2(ex2(a), ex2(c));
+          }
+          unpack2(e2, s[b][j], s[b][j + 1]);
+          acc = add2(acc, e2);
+        }
       }
-      sum[j] = acc;
+      unpack2(acc, sum[j], sum[j + 1]);
     }
   }
   // P^T rows (keys) -> the dead Q image, V-image layout: 64-byte rows, SWIZZLE_64B

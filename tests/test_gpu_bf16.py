@@ -124,6 +124,25 @@ def test_ragged_and_chunked_batches(sd):
     assert O.rel_err_db(y[idx], O.forward(cfg, util.forti_weights(sd), p[idx])) <= -45.0
 
 
+def test_full_size_batch_properties(sd):
+    """BASELINE config 2 at full size (FortiTran, B = 16384, two internal chunks of 8192): determinism, independence of
+    the sequences (permutation equivariance), a checksum against the fp32 path (its own kernels, <= 1e-4 from the
+    reference) and oracle parity on samples taken from both chunks."""
+    w = util.forti_weights(sd)
+    bf = util.make_model("forti", weights=w, precision="bf16")
+    fp = util.make_model("forti", weights=w, precision="fp32")
+    b = 16384
+    p, *_ = O.synthetic_batch(b, seed=41)
+    y = run(bf, p)
+    assert y.shape == (b, 120, 14) and np.isfinite(y.view(np.float32)).all()
+    assert np.array_equal(run(bf, p), y)
+    perm = np.random.default_rng(2).permutation(b)
+    assert np.array_equal(run(bf, p[perm]), y[perm])
+    assert O.rel_err_db(y, run(fp, p)) <= -45.0                       # whole-batch error power vs the fp32 path
+    idx = [0, 5000, 8191, 8192, 12345, b - 1]
+    assert O.rel_err_db(y[idx], O.forward(util.oracle_cfg("forti"), w, p[idx])) <= -45.0
+
+
 def test_host_entry_point_bf16(sd):
     m = util.make_model("ada", weights=sd, precision="bf16")
     p, snr, ds, dop = O.synthetic_batch(2048 + 9, seed=35)

@@ -869,6 +869,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         if (n_seq > 0) mbar_wait_relaxed(misc + MB_X_FREE, (n_seq - 1) & 1);
         mbar_arrive_expect_tx(misc + MB_X_FULL, kXImageBytes);
         bulk_g2s(sb + OFF_X, p.x_images + seq * (int64_t)kXImageBytes, kXImageBytes, misc + MB_X_FULL);
+        // the image of this CTA's next sequence travels HBM -> L2 while this one is processed (the load above is exposed
+        // at every sequence boundary: the residual image has no second buffer)
+        if (seq + gridDim.x < p.nseq) bulk_prefetch_l2(p.x_images + (seq + gridDim.x) * (int64_t)kXImageBytes, kXImageBytes);
         for (int l = 0; l < L; ++l) {
           const TcLayer& W = p.layers[l];
           // the in_proj slot: four head slices per layer, then (FFN) the second K-chunk of each W1 pair

@@ -365,32 +365,23 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {   // 16-byte shared lo
 // QKV accumulators of (head g, row tile t) -> + bias -> bf16 -> Q_g / K_g / V_g images (SWIZZLE_64B rows of 64 B).
 // The 96 accumulator columns [q_g | k_g | v_g] = 12 units of 8 columns, split evenly over the warpgroups.
 constexpr int kQkvUnits = 12 / kParts;
-__device__ __forceinline__ void epi_qkv_store(uint32_t sb, uint32_t bias96, int t, int q, int part, int lane, const uint32_t (&acc)[8 * kQkvUnits]);
-__device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, uint32_t bias96, int t, int q, int part, int lane) {
-  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + t * 96 + part * (8 * kQkvUnits);
-  uint32_t acc[8 * kQkvUnits];
-  tmem_ld_cols(taddr, acc);
-  tmem_wait_ld();
-  epi_qkv_store(sb, bias96, t, q, part, lane, acc);
+// The thread's slice of the in_proj bias (the same 8 * kQkvUnits columns for every row tile): fetched before the
+// accumulators are waited for, so that its shared-memory latency hides under that wait.
+struct QkvBias { uint4 v[2 * kQkvUnits]; };
+__device__ __forceinline__ QkvBias epi_qkv_bias(uint32_t bias96, int part) {
+  QkvBias b;
+#pragma unroll
+  for (int i = 0; i < 2 * kQkvUnits; ++i) b.v[i] = ld_shared_v4(bias96 + (part * kQkvUnits * 2 + i) * 16);
+  return b;
 }
-// row tiles 0 and 1 together: one TMEM round trip instead of two
-__device__ __forceinline__ void epi_qkv_pair(uint32_t tmem, uint32_t sb, uint32_t bias96, int q, int part, int lane) {
-  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + part * (8 * kQkvUnits);
-  uint32_t acc0[8 * kQkvUnits], acc1[8 * kQkvUnits];
-  tmem_ld_cols(taddr, acc0);
-  tmem_ld_cols(taddr + 96, acc1);
-  tmem_wait_ld();
-  epi_qkv_store(sb, bias96, 0, q, part, lane, acc0);
-  epi_qkv_store(sb, bias96, 1, q, part, lane, acc1);
-}
-__device__ __forceinline__ void epi_qkv_store(uint32_t sb, uint32_t bias96, int t, int q, int part, int lane, const uint32_t (&acc)[8 * kQkvUnits]) {
+__device__ __forceinline__ void epi_qkv_store(uint32_t sb, const QkvBias& bias, int t, int q, int part, int lane, const uint32_t (&acc)[8 * kQkvUnits]) {
   const int r = t * 128 + q * 32 + lane;
   const int sw = (r >> 1) & 3;
 #pragma unroll
   for (int i = 0; i < kQkvUnits; ++i) {
     const int u8 = part * kQkvUnits + i;     // unit index inside [q | k | v]
     const int mat = u8 >> 2, u = u8 & 3;     // which matrix, which 16-byte unit of its 64-byte row
-    const uint4 b0 = ld_shared_v4(bias96 + u8 * 32), b1 = ld_shared_v4(bias96 + u8 * 32 + 16);
+    const uint4 b0 = bias.v[2 * i], b1 = bias.v[2 * i + 1];
     const uint32_t* a = acc + i * 8;
     auto sum = [](uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
       return pack_bf16_pair(add2(pack2(__uint_as_float(x0), __uint_as_float(x1)), pack2(__uint_as_float(y0), __uint_as_float(y1))));
@@ -398,6 +389,23 @@ __device__ __forceinline__ void epi_qkv_store(uint32_t sb, uint32_t bias96, int 
     st_shared_v4(sb + OFF_QKV + mat * kQkvPart + r * 64 + ((u ^ sw) << 4), sum(a[0], a[1], b0.x, b0.y), sum(a[2], a[3], b0.z, b0.w),
                  sum(a[4], a[5], b1.x, b1.y), sum(a[6], a[7], b1.z, b1.w));
   }
+}
+__device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, const QkvBias& bias, int t, int q, int part, int lane) {
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + t * 96 + part * (8 * kQkvUnits);
+  uint32_t acc[8 * kQkvUnits];
+  tmem_ld_cols(taddr, acc);
+  tmem_wait_ld();
+  epi_qkv_store(sb, bias, t, q, part, lane, acc);
+}
+// row tiles 0 and 1 together: one TMEM round trip instead of two
+__device__ __forceinline__ void epi_qkv_pair(uint32_t tmem, uint32_t sb, const QkvBias& bias, int q, int part, int lane) {
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + part * (8 * kQkvUnits);
+  uint32_t acc0[8 * kQkvUnits], acc1[8 * kQkvUnits];
+  tmem_ld_cols(taddr, acc0);
+  tmem_ld_cols(taddr + 96, acc1);
+  tmem_wait_ld();
+  epi_qkv_store(sb, bias, 0, q, part, lane, acc0);
+  epi_qkv_store(sb, bias, 1, q, part, lane, acc1);
 }
 
 constexpr int kSmCols = 288 / kParts;   // score columns per thread; the last warpgroup has 8 padding keys (280..287)
@@ -1110,12 +1118,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         for (int g = 0; g < 4; ++g, ++n_head) {
           // ---- QKV epilogue of head g: P.V / score tile #k of this CTA has k = 3 * n_head + t, so k & 1 == (n_head + t) & 1
           tl_event(p, tl, 200 + g, tl_n);   // waiting QKV_DONE
+          mbar_wait(misc + MB_BIAS_FULL + 8 * (g & 1), (n_head >> 1) & 1);   // in_proj bias of this head (buffer g & 1)
+          const QkvBias qb = epi_qkv_bias(qkv_bias + (g & 1) * kQkvBiasBytes, part);
           mbar_wait(misc + MB_QKV_DONE, n_head & 1);
           tc_fence_after_sync();
-          mbar_wait(misc + MB_BIAS_FULL + 8 * (g & 1), (n_head >> 1) & 1);   // in_proj bias of this head (buffer g & 1)
           tl_event(p, tl, 210 + g, tl_n);   // QKV_DONE seen
-          epi_qkv_pair(tmem, sb, qkv_bias + (g & 1) * kQkvBiasBytes, q, part, lane);
-          if (tile2_active) epi_qkv(tmem, sb, qkv_bias + (g & 1) * kQkvBiasBytes, 2, q, part, lane);
+          epi_qkv_pair(tmem, sb, qb, q, part, lane);
+          if (tile2_active) epi_qkv(tmem, sb, qb, 2, q, part, lane);
           tc_fence_before_sync();
           fence_proxy_async_smem();
           warp_arrive(misc + MB_QKV_READY, lane);

@@ -173,8 +173,13 @@ def test_protocol_under_random_delays():
     import json, os, subprocess, sys
     from adafortitran_b200.build import build as build_lib, lib_file
     lib = lib_file("chaos")
-    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(lib_file()):
-        build_lib(variant="chaos")      # missing or older than the product library: rebuild (nvcc, ~2 min)
+    if not os.path.exists(lib):
+        build_lib(variant="chaos")      # normally built by __graft_entry__.build(); nvcc, about a minute
+    elif os.path.getmtime(lib) + 120 < os.path.getmtime(lib_file()):
+        try:                            # clearly older than the product library: refresh it if a compiler is around
+            build_lib(variant="chaos")
+        except Exception:
+            pass
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, AFT_B200_LIB=lib)
     for batch, kind, gate in (("296", "forti", -45.0), ("74", "ada", -36.0)):

@@ -11,7 +11,11 @@ Parity pinning: the reference ships no tests or golden vectors of its own
 reference, executed in the build container from ``/root/reference`` by
 ``tests/golden/make_golden.py`` (committed), whose inputs/weights/outputs are stored
 under ``tests/golden/*.npz``.  ``tests/test_oracle_golden.py`` checks this file
-against those vectors (end-to-end and stage by stage).
+against those vectors (end-to-end and stage by stage).  The same holds for the rows
+either side of the path: ``make_golden_next.py`` records the reference's ``MatDataset`` /
+``extract_values`` / ``LinearEstimator`` (``tests/test_next_rows.py``) and
+``make_golden_generic.py`` its forward at two non-default grids
+(``tests/test_generic_grid.py``).
 
 What it restates (all citations relative to the reference tree):
   * ``src/models/fortitran.py:145-182``   complex -> two real passes -> complex

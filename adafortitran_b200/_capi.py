@@ -10,7 +10,7 @@ import ctypes as C
 import os
 import threading
 
-AFT_ABI_VERSION = 1
+AFT_ABI_VERSION = 2
 AFT_OK = 0
 AFT_ERR_INVALID, AFT_ERR_UNSUPPORTED, AFT_ERR_CUDA, AFT_ERR_WORKSPACE, AFT_ERR_STATE = -1, -2, -3, -4, -5
 AFT_FP32, AFT_BF16 = 0, 1
@@ -51,6 +51,12 @@ class AftWeights(C.Structure):
     ]
 
 
+class AftGather(C.Structure):
+    """Plan of the fused all-gather (``include/aft.h``): gather buffers of all ranks as mapped into this process."""
+    _fields_ = [("peer_out", C.c_void_p * 8), ("world", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int64),
+                ("row0", C.c_int64)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "aft_abi_version": (C.c_int, []),
@@ -63,6 +69,14 @@ EXPORTS = {
                               C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "aft_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_int]),
+    "aft_forward_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(AftGather)]),
+    "aft_forward_host_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int64, C.c_int, C.POINTER(AftGather)]),
+    "aft_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "aft_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "aft_peer_close": (C.c_int, [C.c_void_p]),
+    "aft_peer_free": (C.c_int, [C.c_void_p]),
     "aft_error_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "aft_extract_pilots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "aft_linear_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),

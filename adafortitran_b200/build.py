@@ -121,4 +121,8 @@ def build(force: bool = False, verbose: bool = False, variant: str | None = None
 
 if __name__ == "__main__":
     var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    # ad-hoc experiment variant: --variant=NAME --defs="-DAFT_TC_TAILT=0 ..." builds lib/libaft_b200_NAME.so
+    extra = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--defs=")), None)
+    if var and extra is not None:
+        VARIANTS[var] = extra.split()
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var))

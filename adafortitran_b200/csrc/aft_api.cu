@@ -468,8 +468,60 @@ size_t aft_workspace_bytes(const AftHandle* h, int64_t batch, int precision) {
   return precision == AFT_BF16 ? tc_workspace_bytes(bc) : ws_bytes_f32(bc);
 }
 
+}  // extern "C"
+
+namespace {
+
+// destinations of the chunk that starts at local sample c0: the caller's buffer (if any) and, with a gather plan, this
+// rank's row range in every gather buffer
+int make_dst(const AftHandle* h, float2* out, const AftGather* g, int64_t c0, OutDst* dst) {
+  dst->n = 0;
+  if (out) dst->ptr[dst->n++] = out + c0 * h->pix;
+  if (g) {
+    if (g->world < 1 || g->world > 8 || g->rank < 0 || g->rank >= g->world || g->rows_per_rank < 0 || g->row0 < 0) {
+      set_error("gather plan: bad world / rank / rows_per_rank / row0");
+      return AFT_ERR_INVALID;
+    }
+    for (int p = 0; p < g->world; ++p) {
+      if (!g->peer_out[p]) { set_error("gather plan: NULL gather buffer for rank %d", p); return AFT_ERR_INVALID; }
+      dst->ptr[dst->n++] = static_cast<float2*>(g->peer_out[p]) + (g->rank * g->rows_per_rank + g->row0 + c0) * h->pix;
+    }
+  }
+  if (dst->n == 0) { set_error("aft_forward: no destination (NULL out and no gather plan)"); return AFT_ERR_INVALID; }
+  return AFT_OK;
+}
+
+int forward_impl(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread, const float* doppler,
+                 void* out, int64_t batch, int precision, void* workspace, size_t workspace_bytes, void* stream, const AftGather* gather);
+
+}  // namespace
+
+extern "C" {
+
 int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread, const float* doppler,
                 void* out, int64_t batch, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (h && batch > 0 && !out) { set_error("aft_forward: NULL pilots / out"); return AFT_ERR_INVALID; }
+  return forward_impl(h, pilots, snr, delay_spread, doppler, out, batch, precision, workspace, workspace_bytes, stream, nullptr);
+}
+
+int aft_forward_gather(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread, const float* doppler,
+                       void* out, int64_t batch, int precision, void* workspace, size_t workspace_bytes, void* stream,
+                       const AftGather* gather) {
+  if (!gather) { set_error("aft_forward_gather: NULL gather plan"); return AFT_ERR_INVALID; }
+  if (h && batch + gather->row0 > gather->rows_per_rank) {
+    set_error("aft_forward_gather: rows [%lld, %lld) exceed rows_per_rank %lld", (long long)gather->row0,
+              (long long)(gather->row0 + batch), (long long)gather->rows_per_rank);
+    return AFT_ERR_INVALID;
+  }
+  return forward_impl(h, pilots, snr, delay_spread, doppler, out, batch, precision, workspace, workspace_bytes, stream, gather);
+}
+
+}  // extern "C"
+
+namespace {
+
+int forward_impl(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread, const float* doppler,
+                 void* out, int64_t batch, int precision, void* workspace, size_t workspace_bytes, void* stream, const AftGather* gather) {
   if (!h) { set_error("aft_forward: NULL handle"); return AFT_ERR_INVALID; }
   if (batch < 0) { set_error("aft_forward: negative batch"); return AFT_ERR_INVALID; }
   if (precision != AFT_FP32 && precision != AFT_BF16) { set_error("aft_forward: bad precision %d", precision); return AFT_ERR_INVALID; }
@@ -480,13 +532,15 @@ int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float*
     return AFT_ERR_UNSUPPORTED;
   }
   if (batch == 0) return AFT_OK;
-  if (!pilots || !out) { set_error("aft_forward: NULL pilots / out"); return AFT_ERR_INVALID; }
+  if (!pilots) { set_error("aft_forward: NULL pilots / out"); return AFT_ERR_INVALID; }
   if (h->cfg.adaptive) {
     if (!snr || !delay_spread || !doppler) {
       set_error("aft_forward: meta_data is required when channel adaptation is enabled");
       return AFT_ERR_INVALID;
     }
   }
+  const bool fused = !h->generic && precision == AFT_BF16;   // the tensor-core head stores to all destinations itself
+  if (!fused && !out) { set_error("aft_forward_gather: this path needs a local `out` buffer (the scatter to the peers reads it)"); return AFT_ERR_INVALID; }
   const size_t need = aft_workspace_bytes(h, batch, precision);
   if (!workspace || workspace_bytes < need) {
     set_error("aft_forward: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
@@ -506,6 +560,9 @@ int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float*
     const float* s1 = h->cfg.adaptive ? delay_spread + c0 : nullptr;
     const float* s2 = h->cfg.adaptive ? doppler + c0 : nullptr;
     int rc;
+    OutDst dst;
+    dst.n = 0;
+    if ((fused || gather) && (rc = make_dst(h, fused ? pout : nullptr, gather, c0, &dst)) != AFT_OK) return rc;
     if (h->generic) {
       rc = forward_chunk_generic(h, pin + c0 * h->P, s0, s1, s2, pout + c0 * h->pix, bc, static_cast<float*>(workspace), st);
     } else if (precision == AFT_FP32) {
@@ -513,20 +570,32 @@ int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float*
     } else {
       TcProfileHook hook{h->profile ? &prof_mark_cb : nullptr, h};
       rc = tc_forward_chunk(h->tc, h->front, h->head, h->cfg.activation, h->sm_count, pin + c0 * kPilots, s0, s1, s2,
-                            pout + c0 * kPix, bc, workspace, st, hook) ? AFT_OK : AFT_ERR_CUDA;
+                            dst, bc, workspace, st, hook) ? AFT_OK : AFT_ERR_CUDA;
       if (h->profile) { h->prof_launches[0] += 1; h->prof_launches[1] += 1; h->prof_launches[2] += 1; }
     }
     if (rc != AFT_OK) return rc;
+    if (!fused && gather && !launch_scatter_rows(pout + c0 * h->pix, bc * h->pix, dst, st)) return AFT_ERR_CUDA;
   }
   return AFT_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
 int aft_forward_host(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread,
                      const float* doppler, void* out, int64_t batch, int precision) {
+  if (h && batch > 0 && !out) { set_error("aft_forward_host: NULL pilots / out"); return AFT_ERR_INVALID; }
+  return aft_forward_host_gather(h, pilots, snr, delay_spread, doppler, out, batch, precision, nullptr);
+}
+
+int aft_forward_host_gather(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread,
+                            const float* doppler, void* out, int64_t batch, int precision, const AftGather* gather) {
   if (!h) { set_error("aft_forward_host: NULL handle"); return AFT_ERR_INVALID; }
   if (batch < 0) { set_error("aft_forward_host: negative batch"); return AFT_ERR_INVALID; }
   if (batch == 0) return AFT_OK;
-  if (!pilots || !out) { set_error("aft_forward_host: NULL pilots / out"); return AFT_ERR_INVALID; }
+  if (!pilots || (!out && !gather)) { set_error("aft_forward_host: NULL pilots / out"); return AFT_ERR_INVALID; }
+  if (gather && batch + gather->row0 > gather->rows_per_rank) { set_error("aft_forward_host_gather: rows exceed rows_per_rank"); return AFT_ERR_INVALID; }
   const bool ada = h->cfg.adaptive != 0;
   if (ada && (!snr || !delay_spread || !doppler)) {
     set_error("aft_forward_host: meta_data is required when channel adaptation is enabled");
@@ -570,14 +639,55 @@ int aft_forward_host(AftHandle* h, const void* pilots, const float* snr, const f
       AFT_CUDA(cudaMemcpyAsync(dmeta + ln.cap, delay_spread + c0, bc * sizeof(float), cudaMemcpyHostToDevice, ln.stream));
       AFT_CUDA(cudaMemcpyAsync(dmeta + 2 * ln.cap, doppler + c0, bc * sizeof(float), cudaMemcpyHostToDevice, ln.stream));
     }
-    const int rc = aft_forward(h, din, ada ? dmeta : nullptr, ada ? dmeta + ln.cap : nullptr, ada ? dmeta + 2 * ln.cap : nullptr,
-                               ln.d_out, bc, precision, ln.ws, ln.ws_bytes, ln.stream);
+    AftGather gsub;
+    if (gather) { gsub = *gather; gsub.row0 = gather->row0 + c0; }
+    const int rc = forward_impl(h, din, ada ? dmeta : nullptr, ada ? dmeta + ln.cap : nullptr, ada ? dmeta + 2 * ln.cap : nullptr,
+                                ln.d_out, bc, precision, ln.ws, ln.ws_bytes, ln.stream, gather ? &gsub : nullptr);
     if (rc != AFT_OK) return rc;
-    AFT_CUDA(cudaMemcpyAsync(ho + (size_t)c0 * h->pix * sizeof(float2), ln.d_out, (size_t)bc * h->pix * sizeof(float2),
-                             cudaMemcpyDeviceToHost, ln.stream));
+    if (out)
+      AFT_CUDA(cudaMemcpyAsync(ho + (size_t)c0 * h->pix * sizeof(float2), ln.d_out, (size_t)bc * h->pix * sizeof(float2),
+                               cudaMemcpyDeviceToHost, ln.stream));
   }
   AFT_CUDA(cudaStreamSynchronize(h->lanes[0].stream));
   AFT_CUDA(cudaStreamSynchronize(h->lanes[1].stream));
+  return AFT_OK;
+}
+
+int aft_peer_alloc(size_t bytes, void** dev_ptr, void* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) { set_error("aft_peer_alloc: bad argument"); return AFT_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI documents a 64-byte handle");
+  *dev_ptr = nullptr;
+  AFT_CUDA(cudaMalloc(dev_ptr, bytes));
+  cudaIpcMemHandle_t hd;
+  const cudaError_t e = cudaIpcGetMemHandle(&hd, *dev_ptr);
+  if (e != cudaSuccess) {
+    set_error("aft_peer_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    cudaFree(*dev_ptr);
+    *dev_ptr = nullptr;
+    return AFT_ERR_CUDA;
+  }
+  memcpy(handle64, &hd, sizeof(hd));
+  return AFT_OK;
+}
+
+int aft_peer_open(const void* handle64, void** dev_ptr) {
+  if (!dev_ptr || !handle64) { set_error("aft_peer_open: bad argument"); return AFT_ERR_INVALID; }
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, sizeof(hd));
+  *dev_ptr = nullptr;
+  AFT_CUDA(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return AFT_OK;
+}
+
+int aft_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return AFT_OK;
+  AFT_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return AFT_OK;
+}
+
+int aft_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return AFT_OK;
+  AFT_CUDA(cudaFree(dev_ptr));
   return AFT_OK;
 }
 

@@ -80,6 +80,14 @@ struct HeadPack {
   ConvPack refine;
 };
 
+// Where the head stores the estimates of a chunk: up to 8 destinations (the caller's `out` and, for the fused
+// all-gather of the multi-GPU evaluation path, this rank's row range inside every peer's gather buffer -- peer device
+// memory mapped into this process, written with plain 16-byte stores over NVLink).  ptr[d] addresses sample 0 of the chunk.
+struct OutDst {
+  float2* ptr[9];
+  int n;
+};
+
 // ---------------------------------------------------------------------------------------------
 // launch bookkeeping / error plumbing (aft_api.cu)
 // ---------------------------------------------------------------------------------------------
@@ -106,7 +114,7 @@ void conv_tc_dump_timeline();
 bool conv_tc_pack(const ConvPack& src, void* dst, cudaStream_t st);
 bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilots, const float* snr, const float* ds,
                         const float* dop, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st);
-bool launch_head_tc(const HeadPack& p, const void* pack, const void* himg, const float* enh, float2* out, int64_t nsamples,
+bool launch_head_tc(const HeadPack& p, const void* pack, const void* himg, const float* enh, const OutDst& out, int64_t nsamples,
                     int sm_count, cudaStream_t st);
 
 // gemm_f32.cu : C[M,N] = A[M,K] * W[N,K]^T + bias, fp32 FMA
@@ -132,6 +140,8 @@ bool launch_generic_head(const HeadPack& p, const float* h, const float* enh, fl
 
 // reduce.cu
 bool launch_error_sums(const float2* est, const float2* truth, int64_t count, double* sums, cudaStream_t st);
+// copies src[count] (complex64) to every destination of `dst` with 16-byte accesses (peer scatter of the non-fused paths)
+bool launch_scatter_rows(const float2* src, int64_t count, const OutDst& dst, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers

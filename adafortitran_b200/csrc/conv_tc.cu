@@ -160,7 +160,7 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
 
 __global__ void __launch_bounds__(kThreads, 1)
 head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __restrict__ himg, const float* __restrict__ enh,
-               float* __restrict__ out /* interleaved re/im */, int64_t nsamples) {
+               OutDst out /* complex64 destinations, see aft_internal.cuh */, int64_t nsamples) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   if ((sb & 1023u) != 0) __trap();
@@ -183,6 +183,7 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
   auto img_addr = [&](uint32_t o) -> uint32_t { return sb + OFF_MID + (1 + (o >> 15)) * kPlaneBytes + kPosGuard * 16 + (o & 32767u); };
   const float* es = reinterpret_cast<const float*>(smem + OFF_KEEP + 4096);
   float* w2s = reinterpret_cast<float*>(smem + OFF_KEEP);   // linear_2 weights, [128][8] (k-major, 6 used), loaded once per CTA
+  float* re_keep = reinterpret_cast<float*>(smem + OFF_KEEP + 12288);   // real part of the sample (result of the first pass), [1680]
   for (int i = tid; i < kD * 8; i += kThreads) {
     const int k = i >> 3, f = i & 7;
     w2s[i] = f < kPatchLen ? p.l2_w[f * kD + k] : 0.f;
@@ -267,8 +268,18 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
 #ifdef AFT_TC_TIMELINE
       if (st_on) g_conv_tl[22] = clock64();
 #endif
-      // torch.complex (fortitran.py:180): this pass owns the real or the imaginary half of every element
-      for (int i = tid; i < kPix; i += kThreads) out[(sample * kPix + i) * 2 + part] = res[i];
+      // torch.complex (fortitran.py:180): the real pass parks its result in shared memory; the imaginary pass stores
+      // both as interleaved complex64, 16 bytes (two estimates) per access, to every destination (the caller's buffer
+      // and, in the fused all-gather, the peers' gather buffers over NVLink)
+      if (part == 0) {
+        for (int i = tid; i < kPix; i += kThreads) re_keep[i] = res[i];
+      } else {
+        for (int i = tid; i < kPix / 2; i += kThreads) {
+          const float2 re2 = reinterpret_cast<const float2*>(re_keep)[i], im2 = reinterpret_cast<const float2*>(res)[i];
+          const float4 v = make_float4(re2.x, im2.x, re2.y, im2.y);
+          for (int d = 0; d < out.n; ++d) reinterpret_cast<float4*>(out.ptr[d] + sample * kPix)[i] = v;
+        }
+      }
       __syncthreads();
 #ifdef AFT_TC_TIMELINE
       if (st_on) g_conv_tl[23] = clock64();
@@ -338,7 +349,7 @@ bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilo
   return check_launch("frontend_tc_kernel");
 }
 
-bool launch_head_tc(const HeadPack& p, const void* pack, const void* himg, const float* enh, float2* out, int64_t nsamples,
+bool launch_head_tc(const HeadPack& p, const void* pack, const void* himg, const float* enh, const OutDst& out, int64_t nsamples,
                     int sm_count, cudaStream_t st) {
   if (cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStackSmemBytes) != cudaSuccess) {
     set_error("head_tc: cannot opt in to %d bytes of shared memory: %s", kStackSmemBytes, cudaGetErrorString(cudaGetLastError()));
@@ -346,7 +357,7 @@ bool launch_head_tc(const HeadPack& p, const void* pack, const void* himg, const
   }
   if (nsamples <= 0) return true;
   head_tc_kernel<<<(unsigned)(nsamples < sm_count ? nsamples : sm_count), kThreads, kStackSmemBytes, st>>>(
-      p, static_cast<const uint8_t*>(pack), static_cast<const uint8_t*>(himg), enh, reinterpret_cast<float*>(out), nsamples);
+      p, static_cast<const uint8_t*>(pack), static_cast<const uint8_t*>(himg), enh, out, nsamples);
   count_launch();
   return check_launch("head_tc_kernel");
 }

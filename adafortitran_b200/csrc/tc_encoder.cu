@@ -62,7 +62,13 @@ using namespace ptx;
 #define AFT_TC_GELU_TANH 1  // 1: GELU through one MUFU.TANH (erf-fitted odd polynomial argument), 0: erf by Abramowitz-Stegun (2 MUFU)
 #endif
 #ifndef AFT_TC_TAILT
-#define AFT_TC_TAILT 1      // 1: the 24-row tail tile of every head is processed in transposed form (see "tail tile" below)
+#define AFT_TC_TAILT 2      // tail tile (query rows 256..279) of every head -- 0: as a third row tile (one lane quadrant works),
+                            // 1: transposed (S^T, keys on the lanes), 2: sliced over the lane quadrants (see "tail tile, sliced")
+#endif
+#ifndef AFT_TC_SLICE2
+#define AFT_TC_SLICE2 0     // 1: the third row tile (rows 256..279) of the linear GEMMs is issued as N = 32 column slices, slice q with
+                            // its A operand starting 32 q rows earlier, so that quadrant q's lanes receive columns 32 q .. 32 q + 31 of
+                            // the tail rows and all four sub-partitions share that tile's epilogue (see "third row tile, sliced")
 #endif
 constexpr int kParts = AFT_TC_PARTS;   // threads per accumulator row = compute warpgroups (2: 8 warps x 224 regs, 4: 16 warps x 104 regs)
 static_assert(kParts == 2 || kParts == 4, "kParts must be 2 or 4");
@@ -124,6 +130,19 @@ constexpr uint32_t MISC_TMEM_PTR = MISC_XMAX;   // start-up only: read by every 
 constexpr uint32_t MISC_XSUM = MISC_XMAX + kXchgArray;   // exchange array 1 (softmax sums / LayerNorm sums of squares)
 
 constexpr uint32_t TM_S = 0, TM_P = 288, TM_O = 432, TM_QKV = 0, TM_OUT = 0, TM_F1 = 384;
+// Accumulator columns of the QKV projection of (head g, row tile t).  Head 0 follows LayerNorm2 tile by tile and uses
+// columns t * 96 (inside the out_proj / FFN2 accumulators that LayerNorm2 has released up to that tile).  With the sliced
+// tail (AFT_TC_TAILT == 2) the tail scores of head g - 1 occupy all score columns, so for g > 0 tile 0 goes to the P
+// columns -- free as soon as P.V of the second score tile has completed: the tail's P lives in shared memory -- and is
+// issued BEFORE the tail's scores are read; tiles 1 and 2 follow in columns 0 and 96 while the tail's softmax runs.
+__device__ __forceinline__ uint32_t qkv_col(int g, int t) {
+#if AFT_TC_TAILT == 2
+  return g == 0 ? (uint32_t)(t * 96) : (t == 0 ? TM_P : (uint32_t)((t - 1) * 96));
+#else
+  (void)g;
+  return (uint32_t)(t * 96);
+#endif
+}
 
 constexpr uint32_t kIdescQkv = make_idesc_bf16(128, 96, false, false);
 constexpr uint32_t kIdescS = make_idesc_bf16(128, 144, false, false);
@@ -133,7 +152,10 @@ constexpr uint32_t kIdescST = make_idesc_bf16(128, 32, false, false);   // S^T b
 #ifndef AFT_TC_OT_M
 #define AFT_TC_OT_M 64
 #endif
-constexpr uint32_t kIdescOT = make_idesc_bf16(AFT_TC_OT_M, 32, true, true);   // O^T: A = V^T (MN-major; only rows 0..31 = head dim matter), B = P^T (MN-major)
+constexpr uint32_t kIdescOT = make_idesc_bf16(AFT_TC_OT_M, 32, true, true);
+constexpr uint32_t kIdescS96 = make_idesc_bf16(128, 96, false, false), kIdescS64 = make_idesc_bf16(128, 64, false, false);   // sliced tail: key slices
+constexpr uint32_t kIdescN32 = make_idesc_bf16(128, 32, false, false);   // column slices of the third row tile
+constexpr uint32_t kIdescPT = make_idesc_bf16(64, 32, false, true);    // sliced tail: O = P (image, K-major, M = 64) . V (MN-major)   // O^T: A = V^T (MN-major; only rows 0..31 = head dim matter), B = P^T (MN-major)
 // Tail tile exchange arrays ([4 quadrants][32 queries] f32 each): the padding rows 280..287 of the O image, chunk 0.
 // Those rows are never written during attention by the transposed path and out_proj only turns them into padding rows.
 constexpr uint32_t OFF_XT_MAX = OFF_O + 280 * 128, OFF_XT_SUM = OFF_XT_MAX + 512;
@@ -296,6 +318,20 @@ __device__ __forceinline__ void issue_gemm_sw128(uint32_t tmem, uint32_t d_col, 
     mma_ss(tmem + d_col, ((uint64_t)kHi << 32) | a, ((uint64_t)kHi << 32) | b, idesc, accumulate_first || ks > 0, el);
   }
 }
+// ---- third row tile, sliced (AFT_TC_SLICE2).  Only rows 256..279 of the third M = 128 row tile exist, and TMEM lane
+// quadrant q can only be read by the warps of sub-partition q: as one MMA the tile keeps a single sub-partition busy
+// through every epilogue (bias, LayerNorm, GELU) while the other three wait.  Row i of the A operand lands on lane i,
+// so the tile is issued as `nslices` N = 32 MMAs instead: slice q reads its A rows from 32 q rows EARLIER (tail rows on
+// the lanes of quadrant q; the rows in front are other tokens, their results are never read) and rows 32 q .. 32 q + 31
+// of B, and writes accumulator columns d_col + 32 q.  Quadrant q then owns output columns 32 q .. 32 q + 31 of the tail.
+// `a_row256` / `b_base`: shared addresses of row 256 of the A image and of row 0 of the B image (128-byte rows).
+__device__ __forceinline__ void issue_gemm_sw128_tail(uint32_t tmem, uint32_t d_col, uint32_t a_row256, uint32_t a_chunk_bytes,
+                                                      uint32_t b_base, uint32_t b_chunk_bytes, int ksteps, int nslices,
+                                                      bool accumulate_first, bool el = true) {
+  for (int qq = 0; qq < nslices; ++qq)
+    issue_gemm_sw128(tmem, d_col + 32 * qq, a_row256 - 4096 * qq, a_chunk_bytes, b_base + 4096 * qq, b_chunk_bytes, ksteps, kIdescN32,
+                     accumulate_first, el);
+}
 // Descriptors of the attention operands: constant high word (SBO | version | swizzle), low word = LBO | address >> 4,
 // so that stepping through an operand is one 32-bit add per MMA.
 constexpr uint32_t kDescHiSw64 = (uint32_t)(((uint64_t)(512 >> 4)) | ((uint64_t)1 << 14) | ((uint64_t)kSwizzle64 << 29));
@@ -345,6 +381,34 @@ __device__ __forceinline__ void issue_pv_tail(uint32_t tmem, uint32_t sb, int ob
   for (int ks = 0; ks < 18; ++ks) mma_ss(d, desc_sw64(v + ks * 64), desc_sw64(pt + ks * 64), kIdescOT, ks > 0, el);
 }
 
+// ---- tail tile, sliced (AFT_TC_TAILT == 2).  Row i of an M = 128 A operand lands on TMEM lane i, and the A operand
+// is addressed by its first row: starting the Q image 32 q rows EARLIER puts the tail queries 256..279 on the lanes of
+// quadrant q (rows in front of them are other queries, their results are never read).  The tail scores are issued as
+// four such MMAs over disjoint key slices -- quadrant 0: keys [0, 96), quadrants 1..3: 64 keys each -- into the
+// ordinary score columns, so that every sub-partition owns a quarter of the tail's exponentials in the ordinary
+// row-major form (no cross-lane reductions).  P goes to shared memory as a K-major SWIZZLE_64B A-operand image over
+// the dead Q image (nine 32-key chunks of 32 rows x 64 B; an MMA reads past its chunk into the following ones: only
+// rows 0..23 matter), and O_tail = P . V runs as M = 64 MMAs into the usual accumulator columns.
+__device__ __forceinline__ int tail_key0(int q) { return q == 0 ? 0 : 32 + 64 * q; }   // 0, 96, 160, 224
+__device__ __forceinline__ void issue_scores_tail_sliced(uint32_t tmem, uint32_t sb, bool el = true) {
+#pragma unroll
+  for (int qq = 0; qq < 4; ++qq) {
+    const int key0 = qq == 0 ? 0 : 32 + 64 * qq;
+    const uint32_t a = desc_lo_k64(sb + OFF_QKV + (256 - 32 * qq) * 64);
+    const uint32_t k = desc_lo_k64(sb + OFF_QKV + kQkvPart + key0 * 64);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      mma_ss(tmem + TM_S + key0, desc_sw64(a + ks * 2), desc_sw64(k + ks * 2), qq == 0 ? kIdescS96 : kIdescS64, ks > 0, el);
+  }
+}
+__device__ __forceinline__ void issue_pv_tail_sliced(uint32_t tmem, uint32_t sb, int obuf, bool el = true) {
+  const uint32_t v = desc_lo_mn64(sb + OFF_QKV + 2 * kQkvPart);
+  const uint32_t d = tmem + TM_O + obuf * 32;
+#pragma unroll
+  for (int ks = 0; ks < 18; ++ks)
+    mma_ss(d, desc_sw64(desc_lo_k64(sb + OFF_QKV + (ks >> 1) * 2048) + (ks & 1) * 2), desc_sw64(v + ks * 64), kIdescPT, ks > 0, el);
+}
+
 // =============================================================================================
 // compute-warp epilogues.  q = warp % 4 (TMEM lane quadrant), part = compute warpgroup (0 .. kParts-1): the kParts
 // threads that own TMEM lane `rt` (one per warpgroup) split every accumulator row by columns.
@@ -390,19 +454,19 @@ __device__ __forceinline__ void epi_qkv_store(uint32_t sb, const QkvBias& bias, 
                  sum(a[4], a[5], b1.x, b1.y), sum(a[6], a[7], b1.z, b1.w));
   }
 }
-__device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, const QkvBias& bias, int t, int q, int part, int lane) {
-  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + t * 96 + part * (8 * kQkvUnits);
+__device__ __forceinline__ void epi_qkv(uint32_t tmem, uint32_t sb, const QkvBias& bias, int g, int t, int q, int part, int lane) {
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + qkv_col(g, t) + part * (8 * kQkvUnits);
   uint32_t acc[8 * kQkvUnits];
   tmem_ld_cols(taddr, acc);
   tmem_wait_ld();
   epi_qkv_store(sb, bias, t, q, part, lane, acc);
 }
 // row tiles 0 and 1 together: one TMEM round trip instead of two
-__device__ __forceinline__ void epi_qkv_pair(uint32_t tmem, uint32_t sb, const QkvBias& bias, int q, int part, int lane) {
-  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_QKV + part * (8 * kQkvUnits);
+__device__ __forceinline__ void epi_qkv_pair(uint32_t tmem, uint32_t sb, const QkvBias& bias, int g, int q, int part, int lane) {
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + part * (8 * kQkvUnits);
   uint32_t acc0[8 * kQkvUnits], acc1[8 * kQkvUnits];
-  tmem_ld_cols(taddr, acc0);
-  tmem_ld_cols(taddr + 96, acc1);
+  tmem_ld_cols(taddr + qkv_col(g, 0), acc0);
+  tmem_ld_cols(taddr + qkv_col(g, 1), acc1);
   tmem_wait_ld();
   epi_qkv_store(sb, bias, 0, q, part, lane, acc0);
   epi_qkv_store(sb, bias, 1, q, part, lane, acc1);
@@ -513,8 +577,8 @@ __device__ __forceinline__ void epi_o(uint32_t tmem, uint32_t sb, int g, int t, 
   tmem_wait_ld();
   epi_o_store(sb, g, t, inv_l, q, part, lane, a);
 }
-__device__ __forceinline__ void epi_o_store(uint32_t sb, int g, int t, float inv_l, int q, int part, int lane, const uint32_t (&a)[kOCols]) {
-  const int r = t * 128 + q * 32 + lane;
+// one O image row r: this thread's kOCols accumulator columns (warpgroup `part`) of head g, scaled by 1 / l
+__device__ __forceinline__ void epi_o_store_row(uint32_t sb, int g, int r, float inv_l, int part, const uint32_t (&a)[kOCols]) {
   const uint32_t row = sb + OFF_O + (g >> 1) * kXChunkBytes + r * 128;
 #pragma unroll
   for (int i = 0; i < kOCols / 8; ++i) {
@@ -523,6 +587,9 @@ __device__ __forceinline__ void epi_o_store(uint32_t sb, int g, int t, float inv
     auto sc = [&](int j) { return pack_bf16_pair(mul2(pack2(__uint_as_float(a[8 * i + j]), __uint_as_float(a[8 * i + j + 1])), il)); };
     st_shared_v4(row + ((u ^ (r & 7)) << 4), sc(0), sc(2), sc(4), sc(6));
   }
+}
+__device__ __forceinline__ void epi_o_store(uint32_t sb, int g, int t, float inv_l, int q, int part, int lane, const uint32_t (&a)[kOCols]) {
+  epi_o_store_row(sb, g, t * 128 + q * 32 + lane, inv_l, part, a);
 }
 
 // ---- tail tile, transposed (see issue_scores_tail)
@@ -669,6 +736,90 @@ __device__ __forceinline__ void epi_o_tail(uint32_t tmem, uint32_t sb, int g, in
   }
 }
 
+// ---- tail tile, sliced (see issue_scores_tail_sliced).  Thread (q, part, lane) owns tail query 256 + lane and NC keys:
+// tail_key0(q) + part * NC ...  The 16 threads of a row (4 quadrants x 4 warpgroups) exchange their partial maxima /
+// sums through the ordinary exchange arrays, each thread using the slot it also owns in the full tiles ([part][32 q +
+// lane]): a warp only overwrites slots of its own quadrant, whose previous readers (the quadrant's warps, second named
+// barrier of tile 1) are behind it, and the next full-tile writers are a whole QKV hand-shake away.
+constexpr int kTailBar = 11;   // named barrier of all compute warps: tail maxima exchanged
+template <int NC>
+__device__ __forceinline__ void softmax_tail_sliced_impl(uint32_t tmem, uint32_t sb, uint32_t miscb, uint32_t s_loaded_bar, int q, int part, int lane) {
+  static_assert(NC % 8 == 0, "a thread's keys must be whole 16-byte units of the P image");
+  const int key0 = tail_key0(q) + part * NC;
+  float v[NC];
+  {
+    uint32_t x[NC];
+    tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_S + key0, x);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(x[j]);
+  }
+  if (key0 + NC > kS) {   // keys 280..287 are padding (last warpgroup of quadrant 3)
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (key0 + j >= kS) v[j] = -INFINITY;
+  }
+  float m = fmaxf(v[0], v[1]);
+#pragma unroll
+  for (int j = 2; j < NC; j += 2) m = fmaxf(m, fmaxf(v[j], v[j + 1]));
+  const uint32_t own = (uint32_t)(part * 512 + (q * 32 + lane) * 4);
+  st_shared_f32(miscb + MISC_XMAX + own, m);
+  tc_fence_before_sync();
+  warp_arrive(s_loaded_bar, lane);
+  named_bar_sync(kTailBar, 32 * kComputeWarps);
+#pragma unroll
+  for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) m = fmaxf(m, ld_shared_f32(miscb + MISC_XMAX + pp * 512 + (qq * 32 + lane) * 4));
+  const f32x2 negm2 = pack2(-m, -m);
+  f32x2 s2 = pack2(0.f, 0.f);
+  uint32_t pk[NC / 2];
+#pragma unroll
+  for (int j = 0; j < NC / 2; ++j) {
+    const f32x2 x2 = add2(pack2(v[2 * j], v[2 * j + 1]), negm2);
+    f32x2 e2;
+    if (AFT_TC_POLY_EXP > 0 && j % 3 == 2) {
+      e2 = ex2_poly2(x2);
+    } else {
+      float a, b;
+      unpack2(x2, a, b);
+      e2 = pack2(ex2(a), ex2(b));
+    }
+    s2 = add2(s2, e2);
+    pk[j] = pack_bf16_pair(e2);
+  }
+  // P row `lane`, keys key0 .. key0 + NC: 32-key chunks of 32 rows x 64 B (SWIZZLE_64B, 16-byte units of 8 keys)
+#pragma unroll
+  for (int u = 0; u < NC / 8; ++u) {
+    const int key = key0 + 8 * u;
+    st_shared_v4(sb + OFF_QKV + (key >> 5) * 2048 + lane * 64 + ((((key & 31) >> 3) ^ ((lane >> 1) & 3)) << 4), pk[4 * u], pk[4 * u + 1],
+                 pk[4 * u + 2], pk[4 * u + 3]);
+  }
+  float sa, sb2;
+  unpack2(s2, sa, sb2);
+  st_shared_f32(miscb + MISC_XSUM + own, sa + sb2);
+}
+__device__ __forceinline__ void softmax_tail_sliced(uint32_t tmem, uint32_t sb, uint32_t miscb, uint32_t s_loaded_bar, int q, int part, int lane) {
+  static_assert(kParts == 4 || AFT_TC_TAILT != 2, "the sliced tail assumes four warpgroups");
+  if (q == 0) softmax_tail_sliced_impl<24>(tmem, sb, miscb, s_loaded_bar, q, part, lane);
+  else softmax_tail_sliced_impl<16>(tmem, sb, miscb, s_loaded_bar, q, part, lane);
+}
+// O_tail accumulator (M = 64: tail query i in lane i % 16 of quadrant i / 16) -> / l -> bf16 -> O image rows 256..279
+__device__ __forceinline__ void epi_o_tail_sliced(uint32_t tmem, uint32_t sb, uint32_t miscb, int g, int obuf, int q, int part, int lane) {
+  uint32_t a[kOCols];
+  tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_O + obuf * 32 + part * kOCols, a);
+  tmem_wait_ld();
+  const int i = q * 16 + lane;
+  if (lane < 16 && i < kS - 256) {
+    float l = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) l += ld_shared_f32(miscb + MISC_XSUM + pp * 512 + (qq * 32 + i) * 4);
+    epi_o_store_row(sb, g, 256 + i, rcp_approx(l), part, a);
+  }
+}
+
 // out_proj / linear2 accumulators (tile t) + bias + residual (X image) -> LayerNorm -> X image in place (+ fp32 rows to
 // h_out after the last layer).  A row is shared by the kParts threads that own TMEM lane `rt`; sum and sum of squares are
 // combined through shared memory (one exchange, one named barrier of the quadrant's warps).
@@ -747,6 +898,113 @@ __device__ __forceinline__ void epi_ln(uint32_t tmem, uint32_t sb, uint32_t vec,
   }
   // No trailing barrier: consecutive tiles alternate between two exchange areas (see the call sites), and a warp can only
   // reach tile t + 2 after every warp of its quadrant has passed the barrier of tile t + 1, i.e. finished reading tile t.
+}
+
+// ---- third row tile, sliced: epilogues.  Thread (q, part, lane) owns row 256 + lane and the 8 output columns
+// c0 = 32 q + 8 part ... of it (QKV: quadrant q < 3 holds matrix q of [q | k | v], columns 8 part ...).
+constexpr int kSliceBar = 12;   // named barrier of all compute warps: LayerNorm partial sums of the third row tile exchanged
+__device__ __forceinline__ void epi_qkv_tail(uint32_t tmem, uint32_t sb, uint32_t bias96, int g, int q, int part, int lane) {
+  uint32_t a[8];
+  tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + qkv_col(g, 2) + q * 32 + part * 8, a);
+  const uint4 b0 = ld_shared_v4(bias96 + (q * 32 + part * 8) * 4), b1 = ld_shared_v4(bias96 + (q * 32 + part * 8) * 4 + 16);
+  tmem_wait_ld();
+  const int r = 256 + lane;
+  auto sum = [](uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
+    return pack_bf16_pair(add2(pack2(__uint_as_float(x0), __uint_as_float(x1)), pack2(__uint_as_float(y0), __uint_as_float(y1))));
+  };
+  st_shared_v4(sb + OFF_QKV + q * kQkvPart + r * 64 + ((part ^ ((r >> 1) & 3)) << 4), sum(a[0], a[1], b0.x, b0.y), sum(a[2], a[3], b0.z, b0.w),
+               sum(a[4], a[5], b1.x, b1.y), sum(a[6], a[7], b1.z, b1.w));
+}
+// out_proj / linear2 + bias + residual -> LayerNorm -> X rows 256..279.  The 16 threads of a row exchange their partial
+// sums through `xchg` (two kXchgArray areas), each in the slot it owns in the full tiles ([part][32 q + lane]).
+__device__ __forceinline__ void epi_ln_tail(uint32_t tmem, uint32_t sb, uint32_t vec, int which, int q, int part, int lane, uint32_t xchg) {
+  const int r = 256 + lane, c0 = q * 32 + part * 8;
+  const uint32_t bias = vec + 4 * ((which == 1 ? kVecBOut : kVecBL2) + c0);
+  const uint32_t gam = vec + 4 * ((which == 1 ? kVecN1W : kVecN2W) + c0);
+  const uint32_t bet = vec + 4 * ((which == 1 ? kVecN1B : kVecN2B) + c0);
+  const uint32_t xaddr = sb + OFF_X + (c0 >> 6) * kXChunkBytes + r * 128 + (((((c0 & 63) >> 3)) ^ (r & 7)) << 4);
+  uint32_t acc[8];
+  tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_OUT + 256 + c0, acc);
+  const uint4 xr = ld_shared_v4(xaddr);
+  const uint4 b0 = ld_shared_v4(bias), b1 = ld_shared_v4(bias + 16);
+  tmem_wait_ld();
+  const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+  const f32x2 bb[4] = {pack2(__uint_as_float(b0.x), __uint_as_float(b0.y)), pack2(__uint_as_float(b0.z), __uint_as_float(b0.w)),
+                       pack2(__uint_as_float(b1.x), __uint_as_float(b1.y)), pack2(__uint_as_float(b1.z), __uint_as_float(b1.w))};
+  f32x2 v[4], s2 = pack2(0.f, 0.f), q2 = pack2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const f32x2 a2 = pack2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+    v[j] = add2(add2(a2, bb[j]), bf16x2_to_f32x2(xw[j]));
+    s2 = add2(s2, v[j]);
+    q2 = fma2(v[j], v[j], q2);
+  }
+  {
+    float sa, sb2, qa, qb;
+    unpack2(s2, sa, sb2);
+    unpack2(q2, qa, qb);
+    st_shared_f32(xchg + (part * 128 + q * 32 + lane) * 4, sa + sb2);
+    st_shared_f32(xchg + kXchgArray + (part * 128 + q * 32 + lane) * 4, qa + qb);
+  }
+  named_bar_sync(kSliceBar, 32 * kComputeWarps);
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      sum += ld_shared_f32(xchg + (pp * 128 + qq * 32 + lane) * 4);
+      sq += ld_shared_f32(xchg + kXchgArray + (pp * 128 + qq * 32 + lane) * 4);
+    }
+  const float mean = sum * (1.0f / 128.0f);
+  const float var = fmaxf(fmaf(-mean, mean, sq * (1.0f / 128.0f)), 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float shift = -mean * rstd;
+  const f32x2 rstd2 = pack2(rstd, rstd), shift2 = pack2(shift, shift);
+  const uint4 g0 = ld_shared_v4(gam), g1 = ld_shared_v4(gam + 16), e0 = ld_shared_v4(bet), e1 = ld_shared_v4(bet + 16);
+  const f32x2 gg[4] = {pack2(__uint_as_float(g0.x), __uint_as_float(g0.y)), pack2(__uint_as_float(g0.z), __uint_as_float(g0.w)),
+                       pack2(__uint_as_float(g1.x), __uint_as_float(g1.y)), pack2(__uint_as_float(g1.z), __uint_as_float(g1.w))};
+  const f32x2 ee[4] = {pack2(__uint_as_float(e0.x), __uint_as_float(e0.y)), pack2(__uint_as_float(e0.z), __uint_as_float(e0.w)),
+                       pack2(__uint_as_float(e1.x), __uint_as_float(e1.y)), pack2(__uint_as_float(e1.z), __uint_as_float(e1.w))};
+  if (r < kS) {   // padding rows 280..287 stay zero
+    f32x2 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fma2(fma2(v[j], rstd2, shift2), gg[j], ee[j]);
+    st_shared_v4(xaddr, pack_bf16_pair(o[0]), pack_bf16_pair(o[1]), pack_bf16_pair(o[2]), pack_bf16_pair(o[3]));
+  }
+}
+// FFN1 accumulators of the third row tile: load + bias, then GELU / ReLU -> hidden image rows 256..279
+__device__ __forceinline__ void act_tail_load(uint32_t tmem, uint32_t vec, int pr, int q, int part, f32x2 (&f)[4]) {
+  const int c0 = q * 32 + part * 8;
+  const uint32_t bias = vec + 4 * (kVecBL1 + pr * 128 + c0);
+  uint32_t a[8];
+  tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_F1 + c0, a);
+  const uint4 b0 = ld_shared_v4(bias), b1 = ld_shared_v4(bias + 16);
+  tmem_wait_ld();
+  f[0] = add2(pack2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack2(__uint_as_float(b0.x), __uint_as_float(b0.y)));
+  f[1] = add2(pack2(__uint_as_float(a[2]), __uint_as_float(a[3])), pack2(__uint_as_float(b0.z), __uint_as_float(b0.w)));
+  f[2] = add2(pack2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack2(__uint_as_float(b1.x), __uint_as_float(b1.y)));
+  f[3] = add2(pack2(__uint_as_float(a[6]), __uint_as_float(a[7])), pack2(__uint_as_float(b1.z), __uint_as_float(b1.w)));
+}
+__device__ __forceinline__ void act_tail_store(uint32_t sb, int act, int q, int part, int lane, f32x2 (&f)[4]) {
+  const int r = 256 + lane, c0 = q * 32 + part * 8;
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (act == AFT_ACT_GELU) {
+      if (AFT_TC_GELU_TANH) {
+        pk[j] = pack_bf16_pair(gelu_tanh2(f[j]));
+      } else {
+        float a, b;
+        unpack2(f[j], a, b);
+        pk[j] = pack_bf16x2(gelu_fast(a), gelu_fast(b));
+      }
+    } else {
+      float a, b;
+      unpack2(f[j], a, b);
+      pk[j] = pack_bf16x2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+    }
+  }
+  if (r < kS) st_shared_v4(sb + OFF_O + (c0 >> 6) * kHidBytes + r * 128 + (((((c0 & 63) >> 3)) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
 }
 
 // FFN1 accumulators (pair pr = hidden units 128 pr .. 128 pr + 127, one row tile), split over the warpgroups: load + bias
@@ -952,8 +1210,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               tc_fence_after_sync();
               tl_event(p, tl, 100 + g, tl_n);   // QKV(g) issue start
             }
-            for (int t = t0; t < t1; ++t)
-              issue_gemm_sw128(tmem, TM_QKV + t * 96, sb + OFF_X + t * 128 * 128, kXChunkBytes, sb + OFF_W, 96 * 128, 8, kIdescQkv, false, el);
+            for (int t = t0; t < t1; ++t) {
+              if (AFT_TC_SLICE2 && t == 2)   // third row tile: one N = 32 slice per matrix (q | k | v) on quadrants 0..2
+                issue_gemm_sw128_tail(tmem, qkv_col(g, 2), sb + OFF_X + 256 * 128, kXChunkBytes, sb + OFF_W, 96 * 128, 8, 3, false, el);
+              else
+                issue_gemm_sw128(tmem, qkv_col(g, t), sb + OFF_X + t * 128 * 128, kXChunkBytes, sb + OFF_W, 96 * 128, 8, kIdescQkv, false, el);
+            }
             if (last) {
               mma_commit(misc + MB_W_EMPTY, el);
               mma_commit(misc + MB_QKV_DONE, el);
@@ -987,7 +1249,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               s_loaded.wait(misc + MB_S_LOADED);      // S(t) is in registers
               tc_fence_after_sync();
               tl_event(p, tl, 130 + t, tl_n);   // S_LOADED(t) seen
-#if AFT_TC_TAILT
+#if AFT_TC_TAILT == 2
+              if (t == 0) { issue_scores(tmem, sb, 1, el); mma_commit(misc + MB_S_DONE, el); }
+              else if (t == 1) { issue_scores_tail_sliced(tmem, sb, el); mma_commit(misc + MB_S_DONE, el); }
+              // the sliced tail scores fill all score columns: row tiles 1 and 2 of the next head's projection follow their
+              // read-out and run under the tail's softmax (tile 0 was issued into the P columns, see below).  Measured:
+              // holding tile 2 back until P.V of the tail has been issued is slower (57.5 vs 56.6 ms per 16384 estimates).
+              else if (g < 3) issue_qkv(g + 1, 1, 3, false, true);
+#elif AFT_TC_TAILT
               if (t == 0) { issue_scores(tmem, sb, 1, el); mma_commit(misc + MB_S_DONE, el); }
               else if (t == 1) {
                 issue_scores_tail(tmem, sb, el);
@@ -1007,13 +1276,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               if (n_pv >= 2) mbar_wait(misc + MB_O_FREE + 8 * (n_pv & 1), ((n_pv >> 1) - 1) & 1);
               tc_fence_after_sync();
               tl_event(p, tl, 140 + t, tl_n);   // P_READY(t) seen, P.V(t) issue start
-#if AFT_TC_TAILT
+#if AFT_TC_TAILT == 2
+              if (t == 2) issue_pv_tail_sliced(tmem, sb, n_pv & 1, el); else issue_pv(tmem, sb, n_pv & 1, el);
+#elif AFT_TC_TAILT
               if (t == 2) issue_pv_tail(tmem, sb, n_pv & 1, el); else issue_pv(tmem, sb, n_pv & 1, el);
 #else
               issue_pv(tmem, sb, n_pv & 1, el);
 #endif
               mma_commit(misc + MB_PV_DONE, el);
               tl_event(p, tl, 150 + t, tl_n);   // P.V(t) issued
+#if AFT_TC_TAILT == 2
+              if (t == 1 && g < 3) {
+                // row tile 0 of the next head's projection -> P columns: P.V(1) (the last reader of P in TMEM for this head)
+                // must have completed; nothing else is pending for this warp until the tail's scores have been read
+                mbar_wait(misc + MB_PV_DONE, n_pv & 1);
+                tc_fence_after_sync();
+                issue_qkv(g + 1, 0, 1, true, false);
+              }
+#endif
               if (g == 3 && t == 2) mma_commit(misc + MB_ATTN_DONE, el);
             }
           }
@@ -1026,8 +1306,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             tl_event(p, tl, 160, tl_n);   // out_proj issue start
             const uint32_t w0 = ring_wait(ring_base + 0), w1 = ring_wait(ring_base + 1);
             for (int t = 0; t < 3; ++t) {   // tile-major: LayerNorm1 of tile 0 starts while tiles 1 and 2 are still in the pipe
-              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + t * 128 * 128, 0, w0, 0, 4, kIdescN128, false, el);
-              issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + kXChunkBytes + t * 128 * 128, 0, w1, 0, 4, kIdescN128, true, el);
+              if (AFT_TC_SLICE2 && t == 2) {
+                issue_gemm_sw128_tail(tmem, TM_OUT + 256, sb + OFF_O + 256 * 128, 0, w0, 0, 4, 4, false, el);
+                issue_gemm_sw128_tail(tmem, TM_OUT + 256, sb + OFF_O + kXChunkBytes + 256 * 128, 0, w1, 0, 4, 4, true, el);
+              } else {
+                issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + t * 128 * 128, 0, w0, 0, 4, kIdescN128, false, el);
+                issue_gemm_sw128(tmem, TM_OUT + t * 128, sb + OFF_O + kXChunkBytes + t * 128 * 128, 0, w1, 0, 4, kIdescN128, true, el);
+              }
               mma_commit(bar2 + MB2_OUT_DONE + 8 * t, el);
             }
             ring_release(ring_base + 0);
@@ -1048,6 +1333,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               tc_fence_after_sync();
               const uint32_t w2a = ring_wait(ring_base + 3 + 3 * pj), w2b = ring_wait(ring_base + 4 + 3 * pj);
               const uint32_t d = tmem + TM_OUT + tj * 128;
+              if (AFT_TC_SLICE2 && tj == 2) {
+                issue_gemm_sw128_tail(tmem, TM_OUT + 256, sb + OFF_O + 256 * 128, 0, w2a, 0, 4, 4, pj > 0, el);
+                issue_gemm_sw128_tail(tmem, TM_OUT + 256, sb + OFF_O + kHidBytes + 256 * 128, 0, w2b, 0, 4, 4, true, el);
+              } else
 #pragma unroll
               for (int cc = 0; cc < 2; ++cc) {
                 const uint32_t a_lo = desc128(sb + OFF_O + cc * kHidBytes + tj * 128 * 128), b_lo = desc128(cc == 0 ? w2a : w2b);
@@ -1072,7 +1361,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               if (pr == 0) mbar_wait(bar2 + MB2_X1_READY + 8 * t, n_layers_done & 1);   // LayerNorm1 rows of this tile are in X
               if (n_f1 >= 1) mbar_wait(misc + MB_F1_FREE, (n_f1 - 1) & 1);
               tc_fence_after_sync();
-              {
+              if (AFT_TC_SLICE2 && t == 2) {
+                issue_gemm_sw128_tail(tmem, TM_F1, sb + OFF_X + 256 * 128, 0, w1a, 0, 4, 4, false, el);
+                issue_gemm_sw128_tail(tmem, TM_F1, sb + OFF_X + kXChunkBytes + 256 * 128, 0, w1b, 0, 4, 4, true, el);
+              } else {
                 const uint32_t a0 = desc128(sb + OFF_X + t * 128 * 128), a1 = desc128(sb + OFF_X + kXChunkBytes + t * 128 * 128);
                 const uint32_t b0 = desc128(w1a), b1 = desc128(w1b);
 #pragma unroll
@@ -1123,8 +1415,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           mbar_wait(misc + MB_QKV_DONE, n_head & 1);
           tc_fence_after_sync();
           tl_event(p, tl, 210 + g, tl_n);   // QKV_DONE seen
-          epi_qkv_pair(tmem, sb, qb, q, part, lane);
-          if (tile2_active) epi_qkv(tmem, sb, qb, 2, q, part, lane);
+          epi_qkv_pair(tmem, sb, qb, g, q, part, lane);
+#if AFT_TC_SLICE2
+          if (q < 3) epi_qkv_tail(tmem, sb, qkv_bias + (g & 1) * kQkvBiasBytes, g, q, part, lane);
+#else
+          if (tile2_active) epi_qkv(tmem, sb, qb, g, 2, q, part, lane);
+#endif
           tc_fence_before_sync();
           fence_proxy_async_smem();
           warp_arrive(misc + MB_QKV_READY, lane);
@@ -1171,8 +1467,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               mbar_wait(misc + MB_S_DONE, (n_head + 2) & 1);
               tc_fence_after_sync();
               tl_event(p, tl, 232, tl_n);       // S^T seen
+#if AFT_TC_TAILT == 2
+              softmax_tail_sliced(tmem, sb, miscb, misc + MB_S_LOADED, q, part, lane);
+#else
               softmax_tail(tmem, sb, misc + MB_S_LOADED, q, part, lane);
-              fence_proxy_async_smem();         // P^T is read by the tensor core
+#endif
+              fence_proxy_async_smem();         // P^T / P is read by the tensor core
               // P.V(1) (long finished): waited for before the arrival so that the PV_DONE barrier can never run two
               // phases ahead of a waiter; its O accumulator is read out right below
               mbar_wait(misc + MB_PV_DONE, (n_head + 1) & 1);
@@ -1185,7 +1485,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
             }
             if (t > 0) {
               if (t == 2) epi_o(tmem, sb, g, 1, (n_head + 1) & 1, inv_prev, q, part, lane);
+#if AFT_TC_TAILT == 2
+              else if (t == 3 && q < 2) epi_o_tail_sliced(tmem, sb, miscb, g, (n_head + 2) & 1, q, part, lane);
+#else
               else if (t == 3 && q < kOtQuads) epi_o_tail(tmem, sb, g, (n_head + 2) & 1, q, part, lane);
+#endif
               tc_fence_before_sync();
               fence_proxy_async_smem();
               warp_arrive(misc + MB_O_FREE + 8 * ((n_head + t - 1) & 1), lane);
@@ -1262,7 +1566,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         mbar_wait(misc + MB_VEC_FULL, n_layer & 1);   // this layer's bias / LayerNorm vectors are in shared memory
 #pragma unroll 1
         for (int t = 0; t < 3; ++t) {   // per row tile: out_proj accumulators in -> LayerNorm1 rows out (FFN1 of the tile may start)
-          if (t < 2 || tile2_active) {
+          if (AFT_TC_SLICE2 && t == 2) {
+            mbar_wait(sb + OFF_BAR2 + MB2_OUT_DONE + 8 * t, n_layer & 1);
+            tc_fence_after_sync();
+            epi_ln_tail(tmem, sb, vec, 1, q, part, lane, miscb + MISC_XMAX);
+          } else if (t < 2 || tile2_active) {
             mbar_wait(sb + OFF_BAR2 + MB2_OUT_DONE + 8 * t, n_layer & 1);
             tc_fence_after_sync();
             epi_ln(tmem, sb, vec, 1, t, q, part, lane, t == 1 ? sb + OFF_LN1_XCHG : miscb + MISC_XMAX, nullptr, -1);
@@ -1281,7 +1589,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
           mbar_wait(misc + MB_F1_DONE, k & 1);
           tc_fence_after_sync();
           tl_event(p, tl, 300 + k, tl_n);   // F1_DONE(k) seen
-          if (active) {   // accumulators defined and consumed inside one branch (see the softmax tiles)
+          if (AFT_TC_SLICE2 && t == 2) {   // third row tile, sliced: every quadrant holds 32 hidden units of the tail rows
+            f32x2 f[4];
+            act_tail_load(tmem, vec, pr, q, part, f);
+            tc_fence_before_sync();
+            warp_arrive(misc + MB_F1_FREE, lane);
+            if (pr == 1) mbar_wait(misc + MB_F2_DONE + 8 * t, 0);
+            act_tail_store(sb, p.activation, q, part, lane, f);
+          } else if (active) {   // accumulators defined and consumed inside one branch (see the softmax tiles)
             f32x2 f[kActCols / 2];
             act_load(tmem, vec, pr, q, part, f);
             tc_fence_before_sync();
@@ -1301,7 +1616,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
         tl_event(p, tl, 340, tl_n);   // LayerNorm2 start
 #pragma unroll 1
         for (int t = 0; t < 3; ++t) {   // per row tile: second completion of the tile's F2_DONE in this layer = final accumulators
-          if (t < 2 || tile2_active) {
+          if (AFT_TC_SLICE2 && t == 2) {
+            mbar_wait(misc + MB_F2_DONE + 8 * t, 1);
+            tc_fence_after_sync();
+            epi_ln_tail(tmem, sb, vec, 2, q, part, lane, miscb + MISC_XMAX);
+          } else if (t < 2 || tile2_active) {
             mbar_wait(misc + MB_F2_DONE + 8 * t, 1);
             tc_fence_after_sync();
             epi_ln(tmem, sb, vec, 2, t, q, part, lane, t == 1 ? sb + OFF_LN_XCHG : miscb + MISC_XMAX, nullptr, -1);
@@ -1475,7 +1794,7 @@ size_t tc_workspace_bytes(int64_t bc) {
 }
 
 bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack& head, int activation, int sm_count,
-                      const float2* pilots, const float* snr, const float* ds, const float* dop, float2* out,
+                      const float2* pilots, const float* snr, const float* ds, const float* dop, const OutDst& out,
                       int64_t nsamples, void* workspace, cudaStream_t st, TcProfileHook hook) {
   auto mark = [&]() { if (hook.mark) hook.mark(hook.ctx, st); };
   const int64_t nseq = 2 * nsamples;
@@ -1626,7 +1945,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_attn_kernel(const char
 
 // which = 3: the transposed tail tile (query rows 256..287) with the production helpers: S^T = K Q_tail^T, softmax over
 // the lanes, P^T -> Q image, O^T = V^T P^T, transposed store into the O image (head 0)
-__global__ void __launch_bounds__(kTcThreads, 1) selftest_tail_kernel(const char* qkv_img, float* s_out, float* o_out) {
+// which = 4: the same tile with the sliced helpers (S slices per lane quadrant, P image in shared memory, M = 64 P.V)
+__global__ void __launch_bounds__(kTcThreads, 1) selftest_tail_kernel(const char* qkv_img, float* s_out, float* o_out, int sliced) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sb = smem_u32(smem_raw);
   if ((sb & 1023u) != 0) __trap();
@@ -1651,11 +1971,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_tail_kernel(const char
       bulk_g2s(sb + OFF_QKV, qkv_img, 3 * kQkvPart, misc + MB_X_FULL);
       mbar_wait(misc + MB_X_FULL, 0);
       tc_fence_after_sync();
-      issue_scores_tail(tmem, sb);
+      if (sliced) issue_scores_tail_sliced(tmem, sb); else issue_scores_tail(tmem, sb);
       mma_commit(misc + MB_S_DONE);
       mbar_wait(misc + MB_P_READY, 0);
       tc_fence_after_sync();
-      issue_pv_tail(tmem, sb, 1);
+      if (sliced) issue_pv_tail_sliced(tmem, sb, 1); else issue_pv_tail(tmem, sb, 1);
       mma_commit(misc + MB_PV_DONE);
     }
   } else {
@@ -1663,20 +1983,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_tail_kernel(const char
     const int q = warp & 3, part = warp >> 2;
     mbar_wait(misc + MB_S_DONE, 0);
     tc_fence_after_sync();
-    for (int b = 0; b < (q == 0 ? 3 : 2); ++b) {   // raw scores
-      uint32_t x[kTq];
-      tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_S + b * 32 + part * kTq, x);
-      tmem_wait_ld();
-      const int key = b * 128 + q * 32 + lane;
-      if (key < kSPad)
-        for (int j = 0; j < kTq; ++j) s_out[key * 32 + part * kTq + j] = __uint_as_float(x[j]);
+    if (sliced) {   // raw scores: thread (q, part, lane) holds query 256 + lane, 16 keys of its quadrant's slice at a time
+      const int nc = q == 0 ? 24 : 16, key0 = tail_key0(q) + part * nc;
+      for (int c0 = 0; c0 < nc; c0 += 8) {
+        uint32_t x[8];
+        tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_S + key0 + c0, x);
+        tmem_wait_ld();
+        for (int j = 0; j < 8; ++j) s_out[(key0 + c0 + j) * 32 + lane] = __uint_as_float(x[j]);
+      }
+      softmax_tail_sliced(tmem, sb, miscb, misc + MB_S_LOADED, q, part, lane);
+    } else {
+      for (int b = 0; b < (q == 0 ? 3 : 2); ++b) {   // raw scores
+        uint32_t x[kTq];
+        tmem_ld_cols(tmem + ((uint32_t)(q * 32) << 16) + TM_S + b * 32 + part * kTq, x);
+        tmem_wait_ld();
+        const int key = b * 128 + q * 32 + lane;
+        if (key < kSPad)
+          for (int j = 0; j < kTq; ++j) s_out[key * 32 + part * kTq + j] = __uint_as_float(x[j]);
+      }
+      softmax_tail(tmem, sb, misc + MB_S_LOADED, q, part, lane);
     }
-    softmax_tail(tmem, sb, misc + MB_S_LOADED, q, part, lane);
     fence_proxy_async_smem();
     warp_arrive(misc + MB_P_READY, lane);
     mbar_wait(misc + MB_PV_DONE, 0);
     tc_fence_after_sync();
-    if (q < kOtQuads) epi_o_tail(tmem, sb, 0, 1, q, part, lane);
+    if (sliced) { if (q < 2) epi_o_tail_sliced(tmem, sb, miscb, 0, 1, q, part, lane); }
+    else if (q < kOtQuads) epi_o_tail(tmem, sb, 0, 1, q, part, lane);
     named_bar_sync(9, 32 * kComputeWarps);
     for (int i = threadIdx.x; i < 24 * 32; i += 32 * kComputeWarps) {
       const int r = 256 + i / 32, c = i % 32;
@@ -1864,7 +2196,7 @@ bool tc_selftest(int which, double* max_err, cudaStream_t st) {
     if (worst_s > 1e-3) { set_error("selftest attn tile %d: scores off by %g (outputs %g)", tile, worst_s, worst_o); }
     return true;
   }
-  if (which == 3) {
+  if (which == 3 || which == 4) {
     std::vector<float> Q(288 * 32), K(288 * 32), V(288 * 32);
     for (auto& v : Q) v = bf16_round_host(rng.next() * 1.5f);
     for (auto& v : K) v = bf16_round_host(rng.next() * 1.5f);
@@ -1889,7 +2221,7 @@ bool tc_selftest(int which, double* max_err, cudaStream_t st) {
     cudaMemsetAsync(dO, 0, 24 * 32 * sizeof(float), st);
     cudaMemcpyAsync(di, img.data(), 3 * kQkvPart, cudaMemcpyHostToDevice, st);
     cudaFuncSetAttribute(selftest_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
-    selftest_tail_kernel<<<1, kTcThreads, kTcSmemBytes, st>>>(di, ds, dO);
+    selftest_tail_kernel<<<1, kTcThreads, kTcSmemBytes, st>>>(di, ds, dO, which == 4 ? 1 : 0);
     count_launch();
     std::vector<float> S(288 * 32), O(24 * 32);
     cudaMemcpyAsync(S.data(), ds, S.size() * sizeof(float), cudaMemcpyDeviceToHost, st);

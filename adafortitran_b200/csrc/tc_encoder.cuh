@@ -36,7 +36,7 @@ struct TcProfileHook {
   void* ctx;
 };
 bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack& head, int activation, int sm_count,
-                      const float2* pilots, const float* snr, const float* ds, const float* dop, float2* out,
+                      const float2* pilots, const float* snr, const float* ds, const float* dop, const OutDst& out,
                       int64_t nsamples, void* workspace, cudaStream_t st, TcProfileHook hook);
 bool tc_selftest(int which, double* max_err, cudaStream_t st);
 

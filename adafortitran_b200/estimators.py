@@ -295,9 +295,32 @@ class BaseFortiTranEstimator(nn.Module):
         key = tuple((t.data_ptr(), t._version, t.dtype) for _, t in named)
         return named, key
 
+    def invalidate_weights(self) -> None:
+        """Forget the packed copies of the parameters: the next forward re-reads every parameter.
+
+        The library computes on private packed copies (fp32 re-layouts, bf16 operand images).  They are refreshed
+        automatically when a parameter's storage or version counter changes (``load_state_dict``, optimizer steps,
+        in-place ops on the parameter itself) and after ``load_state_dict`` (post-hook).  Writes that bypass the version
+        counter -- ``p.data.copy_(...)``, ``p.data.mul_(...)``, EMA swaps through ``.data`` -- are invisible to that
+        test: call this method after them, or set ``model.weight_check = "checksum"`` (an on-device checksum of all
+        parameters per forward, one small kernel + a 16-byte read-back) or ``"always"`` (repack on every forward)."""
+        self._packed_key = None
+
+    refresh_weights = invalidate_weights
+
+    def _param_checksum(self, named) -> Tuple[float, float]:
+        flat = torch.cat([t.detach().reshape(-1).to(torch.float64) for _, t in named])
+        w = torch.arange(1, flat.numel() + 1, dtype=torch.float64, device=flat.device)
+        return float(flat.sum().item()), float((flat * (w % 8191.0)).sum().item())
+
     def _sync_weights(self) -> None:
         named, key = self._weight_tensors()
-        if key == self._packed_key:
+        mode = getattr(self, "weight_check", "version")
+        if mode not in ("version", "checksum", "always"):
+            raise ValueError(f"weight_check must be 'version', 'checksum' or 'always', got {mode!r}")
+        if mode == "checksum":
+            key = key + (self._param_checksum(named),)
+        if mode != "always" and key == self._packed_key:
             return
         keep = {n: t.detach().to(device=self.device, dtype=torch.float32).contiguous() for n, t in named}
         ptr = lambda n: C.cast(keep[n].data_ptr(), C.POINTER(C.c_float))
@@ -341,11 +364,9 @@ class BaseFortiTranEstimator(nn.Module):
         except KeyError:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, got {self.precision!r}") from None
 
-    # -- forward (fortitran.py:145-182) ---------------------------------------------------------
-    def forward(self, pilot_symbols: torch.Tensor, meta_data: Optional[Tuple] = None) -> torch.Tensor:
-        """``pilot_symbols``: complex [batch, pilot_scs, pilot_symbols]; ``meta_data``: the reference 6-tuple
-        ``(file_no, snr, delay_spread, max_dop_shift, pilot_freq, channel_type)`` (items 1..3 are used).
-        Returns complex64 [batch, ofdm_scs, ofdm_symbols] on ``self.device``."""
+    # -- argument checks shared by every entry point (fortitran.py:157-173) -----------------------
+    def _check_call(self, pilot_symbols: torch.Tensor, meta_data: Optional[Tuple], where: str):
+        """Validates one call and returns ``(batch, meta_1_3)``; ``where`` is "cuda" (forward) or "cpu" (forward_host)."""
         if self.use_channel_adaptation and meta_data is None:
             raise ValueError("meta_data is required when channel adaptation is enabled")
         if not self.use_channel_adaptation and meta_data is not None:
@@ -353,60 +374,116 @@ class BaseFortiTranEstimator(nn.Module):
         if self.training and torch.is_grad_enabled():
             raise RuntimeError("this implementation is inference-only: call model.eval() and/or run under "
                                "torch.no_grad() (the reference training loop is out of scope)")
-        precision = self._precision_code()
-        self._ensure_handle()
-        if not torch.is_complex(pilot_symbols):
-            raise TypeError(f"pilot_symbols must be complex, got {pilot_symbols.dtype}")
+        if not torch.is_tensor(pilot_symbols) or not torch.is_complex(pilot_symbols):
+            raise TypeError(f"pilot_symbols must be a complex tensor, got {getattr(pilot_symbols, 'dtype', type(pilot_symbols))}")
         if pilot_symbols.dim() != 3 or tuple(pilot_symbols.shape[1:]) != self.pilot_size:
             raise ValueError(f"expected pilot_symbols of shape [batch, {self.pilot_size[0]}, {self.pilot_size[1]}], "
                              f"got {tuple(pilot_symbols.shape)}")
+        if where == "cpu" and pilot_symbols.device.type != "cpu":
+            raise ValueError("forward_host expects CPU tensors; use forward() for device tensors")
         batch = pilot_symbols.shape[0]
+        cond = None
+        if self.use_channel_adaptation:
+            if not isinstance(meta_data, (tuple, list)) or len(meta_data) < 4:
+                raise ValueError("meta_data must be the reference tuple (file_no, snr, delay_spread, max_dop_shift, pilot_freq, "
+                                 "channel_type)")
+            cond = list(meta_data[1:4])
+            for t in cond:
+                if not torch.is_tensor(t):
+                    raise TypeError("meta_data entries 1..3 (snr, delay_spread, max_dop_shift) must be tensors")
+                if t.numel() != batch:
+                    raise ValueError(f"meta_data entries must have {batch} elements, got {t.numel()}")
+                if where == "cpu" and t.device.type != "cpu":
+                    raise ValueError("forward_host expects CPU meta_data tensors")
+        return batch, cond
+
+    def _check_host_out(self, out: Optional[torch.Tensor], batch: int) -> torch.Tensor:
+        if out is None:
+            return torch.empty((batch, *self.ofdm_size), dtype=torch.complex64, pin_memory=True)
+        if not torch.is_tensor(out) or out.device.type != "cpu" or out.dtype != torch.complex64 or not out.is_contiguous() \
+                or tuple(out.shape) != (batch, *self.ofdm_size):
+            raise ValueError(f"out must be a contiguous CPU complex64 tensor of shape {(batch, *self.ofdm_size)}, got "
+                             f"{getattr(out, 'dtype', None)} {tuple(getattr(out, 'shape', ()))} on "
+                             f"{getattr(getattr(out, 'device', None), 'type', None)}")
+        return out
+
+    # -- forward (fortitran.py:145-182) ---------------------------------------------------------
+    def forward(self, pilot_symbols: torch.Tensor, meta_data: Optional[Tuple] = None, gather=None) -> torch.Tensor:
+        """``pilot_symbols``: complex [batch, pilot_scs, pilot_symbols]; ``meta_data``: the reference 6-tuple
+        ``(file_no, snr, delay_spread, max_dop_shift, pilot_freq, channel_type)`` (items 1..3 are used).
+        Returns complex64 [batch, ofdm_scs, ofdm_symbols] on ``self.device``.
+
+        ``gather`` (keyword, optional; not part of the reference signature): a
+        :class:`adafortitran_b200.distributed.PeerGather`; the kernel that writes the estimates then also stores them into
+        every rank's gather buffer (fused all-gather over NVLink) and the returned tensor is this rank's slice of the
+        local gather buffer."""
+        precision = self._precision_code()
+        batch, cond_in = self._check_call(pilot_symbols, meta_data, "cuda")
+        self._ensure_handle()
         with torch.cuda.device(self.device):
             pilots = pilot_symbols.to(device=self.device, dtype=torch.complex64).contiguous()
             cond = [None, None, None]
-            if self.use_channel_adaptation:
-                _, snr, delay_spread, max_dop_shift, _, _ = meta_data
-                cond = [t.to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
-                        for t in (snr, delay_spread, max_dop_shift)]
-                for t in cond:
-                    if t.numel() != batch:
-                        raise ValueError(f"meta_data entries must have {batch} elements, got {t.numel()}")
+            if cond_in is not None:
+                cond = [t.to(device=self.device, dtype=torch.float32).reshape(-1).contiguous() for t in cond_in]
             self._sync_weights()
-            out = torch.empty((batch, *self.ofdm_size), dtype=torch.complex64, device=self.device)
+            if gather is not None:
+                gather.check(self, batch)
+                out = gather.local_rows(batch)
+            else:
+                out = torch.empty((batch, *self.ofdm_size), dtype=torch.complex64, device=self.device)
             if batch == 0:
                 return out
             ws = self._get_workspace(batch, precision)
             ws_ptr = (ws.data_ptr() + 255) // 256 * 256
             stream = torch.cuda.current_stream(self.device).cuda_stream
             vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-            _capi.check(_capi.lib().aft_forward(
-                self._handle, vp(pilots), vp(cond[0]), vp(cond[1]), vp(cond[2]), vp(out), batch, precision,
-                C.c_void_p(ws_ptr), ws.numel() - (ws_ptr - ws.data_ptr()), C.c_void_p(stream)))
+            if gather is None:
+                _capi.check(_capi.lib().aft_forward(
+                    self._handle, vp(pilots), vp(cond[0]), vp(cond[1]), vp(cond[2]), vp(out), batch, precision,
+                    C.c_void_p(ws_ptr), ws.numel() - (ws_ptr - ws.data_ptr()), C.c_void_p(stream)))
+            else:
+                plan = gather.plan()
+                # fused tensor-core path: the head stores straight into the gather buffers; other paths stage in a local buffer
+                fused = precision == _capi.AFT_BF16 and not gather.force_staging
+                stage = None if fused else torch.empty((batch, *self.ofdm_size), dtype=torch.complex64, device=self.device)
+                _capi.check(_capi.lib().aft_forward_gather(
+                    self._handle, vp(pilots), vp(cond[0]), vp(cond[1]), vp(cond[2]), vp(stage), batch, precision,
+                    C.c_void_p(ws_ptr), ws.numel() - (ws_ptr - ws.data_ptr()), C.c_void_p(stream), C.byref(plan)))
         return out
 
     def forward_host(self, pilot_symbols: torch.Tensor, meta_data: Optional[Tuple] = None,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, gather=None) -> torch.Tensor:
         """Host-buffer entry point (``aft_forward_host``): CPU tensors in (pinned for full overlap), CPU complex64
-        estimates out; host<->device copies are chunked and overlapped with compute inside the library."""
-        if self.use_channel_adaptation and meta_data is None:
-            raise ValueError("meta_data is required when channel adaptation is enabled")
+        estimates out; host<->device copies are chunked and overlapped with compute inside the library.  Same argument
+        checks as :meth:`forward`; ``out`` (optional) must be a contiguous CPU complex64 ``[batch, scs, symbols]`` tensor.
+        With ``gather`` the estimates are also stored into every rank's gather buffer (see :meth:`forward`)."""
         precision = self._precision_code()
+        batch, cond_in = self._check_call(pilot_symbols, meta_data, "cpu")
+        out = self._check_host_out(out, batch)
         self._ensure_handle()
         pilots = pilot_symbols.to(dtype=torch.complex64).contiguous()
-        if pilots.device.type != "cpu":
-            raise ValueError("forward_host expects CPU tensors; use forward() for device tensors")
-        batch = pilots.shape[0]
         cond = [None, None, None]
-        if self.use_channel_adaptation:
-            cond = [t.to(dtype=torch.float32).reshape(-1).contiguous() for t in meta_data[1:4]]
-        if out is None:
-            out = torch.empty((batch, *self.ofdm_size), dtype=torch.complex64, pin_memory=True)
+        if cond_in is not None:
+            cond = [t.to(dtype=torch.float32).reshape(-1).contiguous() for t in cond_in]
+        if batch == 0:
+            return out
         with torch.cuda.device(self.device):
             self._sync_weights()
             torch.cuda.current_stream(self.device).synchronize()   # packed weights visible to the internal streams
             vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-            _capi.check(_capi.lib().aft_forward_host(self._handle, vp(pilots), vp(cond[0]), vp(cond[1]), vp(cond[2]),
-                                                     vp(out), batch, precision))
+            if gather is None:
+                _capi.check(_capi.lib().aft_forward_host(self._handle, vp(pilots), vp(cond[0]), vp(cond[1]), vp(cond[2]),
+                                                         vp(out), batch, precision))
+            else:
+                gather.check(self, batch)
+                plan = gather.plan()
+                _capi.check(_capi.lib().aft_forward_host_gather(self._handle, vp(pilots), vp(cond[0]), vp(cond[1]), vp(cond[2]),
+                                                                vp(out), batch, precision, C.byref(plan)))
+        return out
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        out = super()._load_from_state_dict(*args, **kwargs)
+        self._packed_key = None     # load_state_dict: always repack (copy_ into .data would otherwise go unnoticed)
         return out
 
 
@@ -440,6 +517,11 @@ class LinearEstimator(nn.Module):
         self.linear = nn.Linear(self.pilot_size[0] * self.pilot_size[1], self.ofdm_size[0] * self.ofdm_size[1])
         self.to(self.device)
 
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.device = self.linear.weight.device    # follow .to() / .cuda() / .cpu()
+        return out
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         expected = (x.size(0), self.pilot_size[0], self.pilot_size[1])
         if tuple(x.size()) != expected:
@@ -447,16 +529,22 @@ class LinearEstimator(nn.Module):
         if x.is_complex():
             raise RuntimeError("LinearEstimator is a real-valued nn.Linear: complex input has no defined result "
                                "(the reference raises a dtype mismatch inside F.linear)")
-        if self.device.type != "cuda":
-            raise RuntimeError("adafortitran_b200 has no CPU fallback: the model must live on a CUDA device")
+        device = self.linear.weight.device
+        if device.type != "cuda" or self.linear.bias.device != device:
+            raise RuntimeError(f"adafortitran_b200 has no CPU fallback: the parameters live on '{device}', move the model "
+                               "to a CUDA device (.to('cuda'))")
         if self.training and torch.is_grad_enabled():
             raise RuntimeError("adafortitran_b200 is inference-only: call model.eval() or wrap the call in torch.no_grad()")
-        xin = x.to(device=self.device, dtype=torch.float32).reshape(x.size(0), self.linear.in_features).contiguous()
-        out = torch.empty((x.size(0), self.linear.out_features), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+        # the kernel reads fp32, contiguous parameters: convert (no-op for the reference's own layout) instead of
+        # handing over pointers to anything else
+        w = self.linear.weight.detach().to(torch.float32).contiguous()
+        b = self.linear.bias.detach().to(torch.float32).contiguous()
+        xin = x.to(device=device, dtype=torch.float32).reshape(x.size(0), self.linear.in_features).contiguous()
+        out = torch.empty((x.size(0), self.linear.out_features), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
             _capi.check(_capi.lib().aft_linear_forward(
-                C.c_void_p(self.linear.weight.data_ptr()), C.c_void_p(self.linear.bias.data_ptr()), C.c_void_p(xin.data_ptr()),
+                C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(xin.data_ptr()),
                 C.c_void_p(out.data_ptr()), x.size(0), self.linear.in_features, self.linear.out_features, C.c_void_p(stream)))
         return out.reshape(-1, self.ofdm_size[0], self.ofdm_size[1])
 

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define AFT_ABI_VERSION 1
+#define AFT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define AFT_API __attribute__((visibility("default")))
@@ -134,6 +134,39 @@ AFT_API int aft_forward(AftHandle* h, const void* pilots, const float* snr, cons
  * entry point bench.py times as `e2e`. */
 AFT_API int aft_forward_host(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread,
                      const float* doppler, void* out, int64_t batch, int precision);
+
+/* Multi-GPU evaluation path (caller contract: reference src/main/trainer.py:328-347, one process per
+ * GPU, batch-sharded replicas).  The all-gather of the estimates is FUSED into the forward: the kernel that produces
+ * the complex64 estimates stores every 16-byte vector to all `world` gather buffers -- its own and the peers', which are
+ * peer device memory mapped into this process (aft_peer_open) and are written with plain stores over NVLink while the
+ * next samples are being computed.  Local sample i lands at row  rank * rows_per_rank + row0 + i  of every
+ * peer_out[p] (complex64 [world * rows_per_rank, num_scs, num_symbols]).  The stores are complete (and visible to the
+ * peers) when the work enqueued on `stream` has completed on every rank: follow the call with a cross-rank
+ * synchronisation on the same stream (the evaluator's NCCL all-reduce of the error sums does it) before reading. */
+typedef struct AftGather {
+  void* peer_out[8];      /* gather buffer of every rank as seen from THIS process, peer_out[rank] = the local one */
+  int32_t world, rank;    /* 1 <= world <= 8                                                                     */
+  int64_t rows_per_rank;  /* samples per rank in the gathered array                                              */
+  int64_t row0;           /* offset of this call's first sample inside the rank's shard (chunked callers)        */
+} AftGather;
+
+/* aft_forward with the fused all-gather.  `out` may be NULL (the estimates then only go to the gather buffers). */
+AFT_API int aft_forward_gather(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread,
+                const float* doppler, void* out, int64_t batch, int precision,
+                void* workspace, size_t workspace_bytes, void* stream, const AftGather* gather);
+
+/* aft_forward_host with the fused all-gather: host inputs in, estimates of the local shard out to `out` (host, may be
+ * NULL) and to every gather buffer.  Returns after the local work has completed (peers: see above). */
+AFT_API int aft_forward_host_gather(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread,
+                     const float* doppler, void* out, int64_t batch, int precision, const AftGather* gather);
+
+/* Peer-visible device memory for the gather buffers: cudaMalloc + cudaIpcGetMemHandle on the owner, cudaIpcOpenMemHandle
+ * (peer access enabled lazily) on the other ranks of the node.  `handle` is a 64-byte opaque blob the caller moves
+ * between the processes (torch.distributed.all_gather_object in adafortitran_b200/distributed.py). */
+AFT_API int aft_peer_alloc(size_t bytes, void** dev_ptr, void* handle64);
+AFT_API int aft_peer_open(const void* handle64, void** dev_ptr);
+AFT_API int aft_peer_close(void* dev_ptr);
+AFT_API int aft_peer_free(void* dev_ptr);
 
 /* "Next" row N1: the reduction ModelEvaluator._evaluate_dataloader performs right after the
  * forward (reference src/main/trainer.py:338-345 with src/utils.py:164-180): accumulates

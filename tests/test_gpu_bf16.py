@@ -33,7 +33,7 @@ def run(model, pilots, snr=None, ds=None, dop=None):
         return model(torch.from_numpy(pilots), md).cpu().numpy()
 
 
-@pytest.mark.parametrize("which,tol", [(0, 1e-4), (1, 5e-3), (2, 5e-3)])
+@pytest.mark.parametrize("which,tol", [(0, 1e-4), (1, 5e-3), (2, 5e-3), (3, 2e-2), (4, 2e-2)])
 def test_tcgen05_building_blocks(which, tol):
     """UMMA GEMM tile (SWIZZLE_128B K-major descriptors, TMEM loads) and attention tiles (SWIZZLE_64B Q/K, MN-major V,
     P as TMEM A operand) against a double-precision host reference inside the library."""

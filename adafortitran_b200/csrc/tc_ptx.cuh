@@ -54,8 +54,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Record layout: slot [block % 64][warp % 16] = 1<<63 | block<<40 | thread<<24 | parity<<16 | (barrier smem address & 0xFFFF).
 __device__ unsigned long long* g_wait_diag = nullptr;
 
-// Bounded spin: a protocol bug must surface as a trap (reported as a CUDA error), never as a hung GPU.  The first
-// threads to time out leave a record and keep spinning a little so that every stuck role gets to report.
+// Bounded wait: a protocol bug must surface as a trap (reported as a CUDA error), never as a hung GPU.  The first
+// threads to time out leave a record and keep waiting a little so that every stuck role gets to report.
 __device__ __forceinline__ void mbar_wait_timeout(uint32_t bar, uint32_t parity) {
   if (g_wait_diag != nullptr)
     g_wait_diag[(blockIdx.x & 63) * 16 + ((threadIdx.x >> 5) & 15)] =
@@ -65,7 +65,7 @@ __device__ __forceinline__ void mbar_wait_timeout(uint32_t bar, uint32_t parity)
 }
 // -DAFT_TC_CHAOS: every wait is preceded by a pseudo-random, warp-uniform delay of up to ~8 us for one call in four.
 // Shakes the relative timing of the roles (MMA issuer, producer, compute warps); a protocol that relies on timing rather
-// than on its barriers then hangs into the bounded spin below and is reported by the wait-timeout diagnostics.
+// than on its barriers then hangs into the bounded wait below and is reported by the wait-timeout diagnostics.
 __device__ __forceinline__ void chaos_delay() {
 #ifdef AFT_TC_CHAOS
   uint32_t c;
@@ -75,31 +75,49 @@ __device__ __forceinline__ void chaos_delay() {
   if (((h >> 28) & 3) == 0) __nanosleep((h >> 8) & 0x1FFF);
 #endif
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  chaos_delay();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    ++spins;
-    if (spins == 4000000u) mbar_wait_timeout(bar, parity);
-    if (spins > 6000000u) __trap();
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the hint (ns) expires.
+// The plain form returns after a short, implementation-defined time; in a kernel whose roles wait most of the time the
+// resulting poll loops were a quarter of all issued instructions and competed with the working warps of their
+// sub-partition for issue slots (ncu: 12 % of the warp samples "not selected").
+__device__ __forceinline__ bool mbar_try_wait_for(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifndef AFT_TC_WAIT_HINT_NS
+#define AFT_TC_WAIT_HINT_NS 100000u     // suspend hint of one try_wait (100 us)
+#endif
+// Time budget of one wait (wall clock, not poll counts: under compute-sanitizer, a debugger or time slicing a legitimate
+// wait can take arbitrarily many polls).  The chaos build injects up to ~8 us per wait on purpose.
+constexpr unsigned long long kWaitReportNs = 4000000000ull, kWaitTrapNs = 6000000000ull;
+// slow path (rare: the first try_wait already sleeps up to the hint): poll with the hint, watch the wall clock
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  const unsigned long long t0 = global_timer_ns();
+  bool reported = false;
+  while (!mbar_try_wait_for(bar, parity, AFT_TC_WAIT_HINT_NS)) {
+    const unsigned long long dt = global_timer_ns() - t0;
+    if (!reported && dt > kWaitReportNs) { mbar_wait_timeout(bar, parity); reported = true; }
+    if (dt > kWaitTrapNs) __trap();
   }
 }
-
-// same, for waits that are not latency critical (producer): back off between polls so the spin does not steal
-// issue slots from the compute warps sharing the sub-partition
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  chaos_delay();
+  if (!mbar_try_wait_for(bar, parity, AFT_TC_WAIT_HINT_NS)) mbar_wait_slow(bar, parity);
+}
+// same contract; kept as a separate name for the roles whose waits are not latency critical (producer)
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
-    ++spins;
-#ifdef AFT_TC_CHAOS
-    if (spins == 60000000u) mbar_wait_timeout(bar, parity);   // let the stuck compute / MMA roles report first
-    if (spins > 80000000u) __trap();
-#else
-    if (spins == 2000000u) mbar_wait_timeout(bar, parity);
-    if (spins > 3000000u) __trap();
-#endif
-  }
+  if (!mbar_try_wait_for(bar, parity, AFT_TC_WAIT_HINT_NS)) mbar_wait_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------------------------------------

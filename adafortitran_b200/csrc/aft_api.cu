@@ -276,31 +276,52 @@ int forward_chunk_f32(AftHandle* h, const float2* pilots, const float* snr, cons
 }
 
 // ---- shape-generic AFT_FP32 path (generic_f32.cu)
-size_t generic_floats_per_chunk(const AftHandle* h, int64_t bc) {
+size_t generic_floats_per_chunk(const AftHandle* h, int64_t bc, int precision = AFT_FP32) {
   const size_t nseq = 2 * (size_t)bc, M = nseq * h->S;
   size_t f = 0;
   f += align_up(nseq * h->pix, 64);          // enh
   f += align_up(M * kD, 64);                 // h
-  f += align_up(M * 3 * kD, 64);             // qkv (ffn hidden aliases it)
-  f += align_up(M * kD, 64);                 // attention output
+  if (precision == AFT_BF16) {
+    f += align_up(tc_long_workspace_bytes((int64_t)nseq, h->S) / sizeof(float) + 256, 64);   // operand images of tc_long.cu
+  } else {
+    f += align_up(M * 3 * kD, 64);           // qkv (ffn hidden aliases it)
+    f += align_up(M * kD, 64);               // attention output
+  }
   const size_t a = generic_front_scratch_floats(bc, h->P, h->pix, h->S), b = generic_head_scratch_floats(bc, h->pix);
   f += align_up(a > b ? a : b, 64);          // frontend / head scratch (conv planes)
   return f;
 }
 // samples per internal chunk: about 1 GB of scratch, at least one sample
-int64_t generic_chunk(const AftHandle* h) {
-  const size_t per = generic_floats_per_chunk(h, 1) * sizeof(float);
-  int64_t bc = (int64_t)((size_t(1) << 30) / (per ? per : 1));
+int64_t generic_chunk(const AftHandle* h, int precision = AFT_FP32) {
+  // about 1 GB of scratch (3 GB on the tensor-core path, whose kernels want more row tiles per launch), at least one sample
+  const size_t per = generic_floats_per_chunk(h, 1, precision) * sizeof(float);
+  int64_t bc = (int64_t)((size_t(precision == AFT_BF16 ? 3 : 1) << 30) / (per ? per : 1));
   if (bc < 1) bc = 1;
   if (bc > kChunkF32) bc = kChunkF32;
+  if (2 * bc > 65535) bc = 32767;            // sequences are a grid dimension of the attention kernel
   return bc;
 }
 
 int forward_chunk_generic(AftHandle* h, const float2* pilots, const float* snr, const float* ds, const float* dop, float2* out,
-                          int64_t bc, float* ws, cudaStream_t st) {
+                          int64_t bc, float* ws, cudaStream_t st, int precision) {
   const int64_t nseq = 2 * bc, M = nseq * h->S;
   float* enh = ws;
   float* hbuf = enh + align_up((size_t)nseq * h->pix, 64);
+  if (precision == AFT_BF16) {
+    // tensor-core encoder over row-tile operand images (tc_long.cu); frontend and head stay on the shape-generic fp32 kernels
+    float* img = hbuf + align_up((size_t)M * kD, 64);
+    float* scratch = img + align_up(tc_long_workspace_bytes(nseq, h->S) / sizeof(float) + 256, 64);
+    void* img_aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(img) + 1023) & ~uintptr_t(1023));
+    prof_mark(h, st);
+    if (!launch_generic_frontend(h->front, pilots, snr, ds, dop, enh, hbuf, scratch, bc, h->H, h->W, h->P, h->ph, h->pw, st)) return AFT_ERR_CUDA;
+    prof_mark(h, st);
+    if (!tc_long_encoder(h->tc, h->cfg.activation, h->sm_count, hbuf, hbuf, nseq, h->S, img_aligned, st)) return AFT_ERR_CUDA;
+    prof_mark(h, st);
+    if (!launch_generic_head(h->head, hbuf, enh, out, scratch, bc, h->H, h->W, h->ph, h->pw, st)) return AFT_ERR_CUDA;
+    prof_mark(h, st);
+    if (h->profile) { h->prof_launches[0] += 1; h->prof_launches[1] += 2 * (int64_t)h->layers.size() + 2; h->prof_launches[2] += 1; }
+    return AFT_OK;
+  }
   float* qkv = hbuf + align_up((size_t)M * kD, 64);
   float* att = qkv + align_up((size_t)M * 3 * kD, 64);
   float* scratch = att + align_up((size_t)M * kD, 64);
@@ -323,7 +344,7 @@ int forward_chunk_generic(AftHandle* h, const float2* pilots, const float* snr, 
 }
 
 int64_t chunk_for(const AftHandle* h, int precision) {
-  if (h->generic) return generic_chunk(h);
+  if (h->generic) return generic_chunk(h, precision);
   return precision == AFT_BF16 ? kChunkBf16 : kChunkF32;
 }
 
@@ -453,7 +474,7 @@ int aft_load_weights(AftHandle* h, const AftWeights* w, void* stream) {
     for (const auto& it : items)
       if (!copy_to(it.s, it.d, it.n, st, it.name)) return AFT_ERR_CUDA;
   }
-  if (!h->generic && !tc_weights_pack(h->tc, h->layers, h->front.enh, h->head.refine, st)) return AFT_ERR_CUDA;
+  if (!tc_weights_pack(h->tc, h->layers, h->front.enh, h->head.refine, st)) return AFT_ERR_CUDA;
   if (!check_launch("aft_load_weights")) return AFT_ERR_CUDA;
   h->loaded = true;
   return AFT_OK;
@@ -464,7 +485,7 @@ size_t aft_workspace_bytes(const AftHandle* h, int64_t batch, int precision) {
   if (precision != AFT_FP32 && precision != AFT_BF16) { set_error("aft_workspace_bytes: bad precision"); return 0; }
   int64_t bc = batch < chunk_for(h, precision) ? batch : chunk_for(h, precision);
   if (bc < 1) bc = 1;
-  if (h->generic) return generic_floats_per_chunk(h, bc) * sizeof(float);
+  if (h->generic) return generic_floats_per_chunk(h, bc, precision) * sizeof(float);
   return precision == AFT_BF16 ? tc_workspace_bytes(bc) : ws_bytes_f32(bc);
 }
 
@@ -526,11 +547,6 @@ int forward_impl(AftHandle* h, const void* pilots, const float* snr, const float
   if (batch < 0) { set_error("aft_forward: negative batch"); return AFT_ERR_INVALID; }
   if (precision != AFT_FP32 && precision != AFT_BF16) { set_error("aft_forward: bad precision %d", precision); return AFT_ERR_INVALID; }
   if (!h->loaded) { set_error("aft_forward: weights not loaded (call aft_load_weights first)"); return AFT_ERR_STATE; }
-  if (h->generic && precision == AFT_BF16) {
-    set_error("aft_forward: the tensor-core AFT_BF16 path is specialised for the reference default grid (120x14, pilots 12x2, "
-              "patch 3x2); this %dx%d model runs with AFT_FP32 only", h->H, h->W);
-    return AFT_ERR_UNSUPPORTED;
-  }
   if (batch == 0) return AFT_OK;
   if (!pilots) { set_error("aft_forward: NULL pilots / out"); return AFT_ERR_INVALID; }
   if (h->cfg.adaptive) {
@@ -564,7 +580,7 @@ int forward_impl(AftHandle* h, const void* pilots, const float* snr, const float
     dst.n = 0;
     if ((fused || gather) && (rc = make_dst(h, fused ? pout : nullptr, gather, c0, &dst)) != AFT_OK) return rc;
     if (h->generic) {
-      rc = forward_chunk_generic(h, pin + c0 * h->P, s0, s1, s2, pout + c0 * h->pix, bc, static_cast<float*>(workspace), st);
+      rc = forward_chunk_generic(h, pin + c0 * h->P, s0, s1, s2, pout + c0 * h->pix, bc, static_cast<float*>(workspace), st, precision);
     } else if (precision == AFT_FP32) {
       rc = forward_chunk_f32(h, pin + c0 * kPilots, s0, s1, s2, pout + c0 * kPix, bc, static_cast<float*>(workspace), st);
     } else {

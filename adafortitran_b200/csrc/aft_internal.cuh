@@ -122,6 +122,9 @@ enum GemmEpi { kEpiBias = 0, kEpiBiasAct = 1, kEpiBiasResLn = 2 };
 bool launch_gemm_f32(int epi, const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
                      int act, const float* residual, const float* gamma, const float* beta, cudaStream_t st);
 
+// the same product for arbitrary N, K (bias epilogue, guarded edges)
+bool launch_gemm_f32_any(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, cudaStream_t st);
+
 // attn_f32.cu : per (sequence, head) softmax(q k^T / sqrt(dh)) v, fp32
 bool launch_attn_f32(const float* qkv, float* out, int64_t nseq, cudaStream_t st);
 

@@ -110,7 +110,67 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const 
   }
 }
 
+// The same tiling for arbitrary N and K (bias epilogue only): guarded scalar loads / stores at the edges.  Used by the
+// shape-generic frontend for the pilot upsampler Linear(P, H*W) (reference src/models/fortitran.py:86,203), whose extents
+// follow the grid (BASELINE config 5: 3276 -> 45864).
+__global__ void __launch_bounds__(256)
+gemm_f32_edge_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias, float* C, int64_t M, int N, int K) {
+  __shared__ __align__(16) float As[BK][PITCH];
+  __shared__ __align__(16) float Bs[BK][PITCH];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {   // 128 rows x 16 k per operand, k fastest: consecutive threads read consecutive k
+      const int idx = tid + i * 256;
+      const int r = idx >> 4, kk = idx & 15;
+      const bool kin = k0 + kk < K;
+      As[kk][r] = (kin && row0 + r < M) ? A[(row0 + r) * K + k0 + kk] : 0.f;
+      Bs[kk][r] = (kin && col0 + r < N) ? W[(int64_t)(col0 + r) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = row0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (c < N) C[m * N + c] = acc[i][j] + bias[c];
+    }
+  }
+}
+
 }  // namespace
+
+bool launch_gemm_f32_any(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, cudaStream_t st) {
+  if (M <= 0) return true;
+  const dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+  gemm_f32_edge_kernel<<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K);
+  count_launch();
+  return check_launch("gemm_f32_edge_kernel");
+}
 
 bool launch_gemm_f32(int epi, const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
                      int act, const float* residual, const float* gamma, const float* beta, cudaStream_t st) {

@@ -242,7 +242,9 @@ bool launch_generic_frontend(const FrontPack& p, const float2* pilots, const flo
   g_split_pilots<<<nblk(nsamples * P), 256, 0, st>>>(pilots, x, nsamples, P);
   count_launch();
   // generic fp32 linear: up_wt holds the torch layout [pix][P] here (see aft_api.cu)
-  if (!launch_linear(p.up_wt, p.up_b, x, u, nseq, P, pix, st)) return false;
+  // (large extents: the tiled GEMM; the LinearEstimator kernel of aux.cu is built for a few dozen inputs)
+  if ((int64_t)P * pix > (1 << 20) ? !launch_gemm_f32_any(x, p.up_wt, p.up_b, u, nseq, pix, P, st) : !launch_linear(p.up_wt, p.up_b, x, u, nseq, P, pix, st))
+    return false;
   if (!conv_stack(p.enh, u, a, b, enh, nseq, H, W, st)) return false;
   if (p.adaptive) {
     g_adapter<<<dim3((unsigned)nsamples, 3), 256, 0, st>>>(p, snr, ds, dop, z, 2 * S);

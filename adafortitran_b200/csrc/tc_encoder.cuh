@@ -40,4 +40,10 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
                       int64_t nsamples, void* workspace, cudaStream_t st, TcProfileHook hook);
 bool tc_selftest(int which, double* max_err, cudaStream_t st);
 
+// tc_long.cu : the encoder for any sequence length (activations in global memory as per-row-tile operand images,
+// streaming attention).  h_in / h_out: fp32 [nseq * S][128] rows (may alias); workspace of tc_long_workspace_bytes().
+size_t tc_long_workspace_bytes(int64_t nseq, int S);
+bool tc_long_encoder(const TcWeights& w, int activation, int sm_count, const float* h_in, float* h_out, int64_t nseq, int S,
+                     void* workspace, cudaStream_t st);
+
 }  // namespace aft

@@ -112,8 +112,9 @@ bool launch_head(const HeadPack& p, const float* h, const float* enh, float2* ou
 size_t conv_tc_pack_bytes();
 void conv_tc_dump_timeline();
 bool conv_tc_pack(const ConvPack& src, void* dst, cudaStream_t st);
+//   zbuf : [nsamples][3][2 S] fp32 scratch for the adaptive features (written by adapter_kernel; unused for FortiTran)
 bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilots, const float* snr, const float* ds,
-                        const float* dop, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st);
+                        const float* dop, float* zbuf, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st);
 bool launch_head_tc(const HeadPack& p, const void* pack, const void* himg, const float* enh, const OutDst& out, int64_t nsamples,
                     int sm_count, cudaStream_t st);
 

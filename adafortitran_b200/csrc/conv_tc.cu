@@ -13,6 +13,10 @@ using namespace convtc;
 
 namespace {
 
+#ifndef AFT_HEAD_L2_TC
+#define AFT_HEAD_L2_TC 1    // 1: linear_2 of the head as tcgen05 MMAs over the staged encoder image, 0: SIMT dot products
+#endif
+
 // One item = (token row t, 8 consecutive model columns): 288 x 16 items = 9 per thread, processed three at a time so
 // that the six 16-byte reads of the positional table (L2 resident, 143 KB) of a batch are in flight together.
 template <int IN_DIM>
@@ -52,10 +56,54 @@ __device__ __forceinline__ void linear1_image(const float* __restrict__ posb, co
   }
 }
 
+// ChannelAdapter (reference blocks/channel_adaptivity.py:34-40,59-63), once per SAMPLE (the reference evaluates it in both
+// the real and the imaginary pass): z[sample][m][j], m = snr / delay spread / Doppler, j < 2 S.  The last layer
+// (42 x 560 weights per condition, 94 KB) is held in registers -- thread j keeps column j -- and the CTA streams its
+// samples past them, instead of every sequence re-reading 282 KB of weights from L2 inside the frontend kernel.
+constexpr int kAdaThreads = 576;     // >= 2 S = 560 outputs of one encoder
+constexpr int kAdaGroup = 32;        // samples per pass of a CTA
+__global__ void __launch_bounds__(kAdaThreads, 1)
+adapter_kernel(FrontPack p, const float* __restrict__ snr, const float* __restrict__ ds, const float* __restrict__ dop,
+               float* __restrict__ z, int64_t nsamples) {
+  __shared__ float hid2[kAdaGroup][kMaxAdaHidden];
+  const int j = threadIdx.x;
+  const bool live = j < 2 * kS;
+  for (int i = threadIdx.x; i < kAdaGroup * kMaxAdaHidden; i += kAdaThreads) (&hid2[0][0])[i] = 0.f;   // units >= h2 stay zero
+  for (int m = 0; m < 3; ++m) {
+    const MlpPack& mp = p.mlp[m];
+    const float* cond = m == 0 ? snr : (m == 1 ? ds : dop);
+    float w[kMaxAdaHidden];
+#pragma unroll
+    for (int k = 0; k < kMaxAdaHidden; ++k) w[k] = (live && k < p.h2) ? mp.w2t[k * 2 * kS + j] : 0.f;
+    const float b2 = live ? mp.b2[j] : 0.f;
+    for (int64_t s0 = (int64_t)blockIdx.x * kAdaGroup; s0 < nsamples; s0 += (int64_t)gridDim.x * kAdaGroup) {
+      const int ns = (int)(nsamples - s0 < kAdaGroup ? nsamples - s0 : kAdaGroup);
+      __syncthreads();   // the previous group's hidden activations have been consumed
+      // hidden layers of the group's samples: thread (sample, unit) pairs
+      for (int i = threadIdx.x; i < ns * p.h2; i += kAdaThreads) {
+        const int s = i / p.h2, u = i - s * p.h2;
+        const float c = cond[s0 + s];
+        float acc = mp.b1[u];
+        for (int k = 0; k < p.h1; ++k) acc = fmaf(mp.w1[u * p.h1 + k], fmaxf(fmaf(mp.w0[k], c, mp.b0[k]), 0.f), acc);
+        hid2[s][u] = fmaxf(acc, 0.f);
+      }
+      __syncthreads();
+      if (live) {
+        for (int s = 0; s < ns; ++s) {
+          float acc = b2;
+#pragma unroll
+          for (int k = 0; k < kMaxAdaHidden; ++k) acc = fmaf(w[k], hid2[s][k], acc);   // units >= h2: zero weights
+          z[((s0 + s) * 3 + m) * (int64_t)(2 * kS) + j] = acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* __restrict__ pilots, const float* __restrict__ snr,
-                   const float* __restrict__ ds, const float* __restrict__ dop, float* __restrict__ enh_out,
-                   __nv_bfloat16* __restrict__ hb_out, int64_t nseq) {
+frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* __restrict__ pilots, const float* __restrict__ zin,
+                   float* __restrict__ enh_out, __nv_bfloat16* __restrict__ hb_out, int64_t nseq) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   if ((sb & 1023u) != 0) __trap();
@@ -118,24 +166,10 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
     }
     for (int i = tid; i < in_dim * kD; i += kThreads) w1t[i] = p.l1_wt[i];
     if (p.adaptive) {
-      const float cond[3] = {snr[sample], ds[sample], dop[sample]};
-      for (int m = 0; m < 3; ++m) {
-        const MlpPack& mp = p.mlp[m];
-        if (tid < p.h1) hid[tid] = fmaxf(fmaf(mp.w0[tid], cond[m], mp.b0[tid]), 0.f);
-        __syncthreads();
-        if (tid < p.h2) {
-          float acc = mp.b1[tid];
-          for (int k = 0; k < p.h1; ++k) acc = fmaf(mp.w1[tid * p.h1 + k], hid[k], acc);
-          hid[64 + tid] = fmaxf(acc, 0.f);
-        }
-        __syncthreads();
-        for (int j = tid; j < 2 * kS; j += kThreads) {
-          float acc = mp.b2[j];
-          for (int k = 0; k < p.h2; ++k) acc = fmaf(mp.w2t[k * 2 * kS + j], hid[64 + k], acc);
-          z[m * 2 * kS + j] = acc;
-        }
-        __syncthreads();
-      }
+      // adaptive features (fortitran.py:216): computed once per sample by adapter_kernel, 3 x 560 floats
+      const float* zs = zin + sample * (int64_t)(3 * 2 * kS);
+      for (int i = tid; i < 3 * 2 * kS; i += kThreads) z[i] = zs[i];
+      __syncthreads();
       for (int i = tid; i < kS * kAda; i += kThreads) {
         const int t = i / kAda, f = i - t * kAda;
         tok[t * in_dim + kPatchLen + f] = z[(f >> 1) * 2 * kS + 2 * t + (f & 1)];
@@ -166,7 +200,7 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
   if ((sb & 1023u) != 0) __trap();
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar = sb + OFF_BAR;
-  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); mbar_init(bar + 32, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); mbar_init(bar + 32, 1); mbar_init(bar + 40, 1); fence_mbar_init(); }
   if (warp == 1) { tmem_alloc(bar + 16, 512); tmem_relinquish(); }
   stack_init(smem, pack);
   tc_fence_before_sync();
@@ -177,6 +211,99 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
 
   float* in = reinterpret_cast<float*>(smem + OFF_IN);
   const float* res = reinterpret_cast<const float*>(smem + OFF_OUT);
+#if AFT_HEAD_L2_TC
+  // linear_2 on the tensor core.  The encoder's output image (2 K-chunks x 288 rows x 128 B, SWIZZLE_128B) is staged as ONE
+  // contiguous 73,728-byte block starting 1024-aligned inside mid group 1 and running through groups 2 and 3 (dead between
+  // two stack runs): it is then directly the A operand of  D[token, 16] = X[token, 128] . W2^T  (three M = 128 row tiles,
+  // N = 16: six real outputs + zero rows).  The block covers the zero guards between the groups; they are re-zeroed
+  // before the conv stack runs.  W2 lives as a 4 KB bf16 operand image at the start of the persistent scratch.
+  constexpr uint32_t kImgOff = OFF_MID + kPlaneBytes + 1024;
+  static_assert(kImgOff % 1024 == 0 && kImgOff + kXImageBytes <= OFF_MID + 4 * kPlaneBytes, "image staging must be aligned and inside the mid planes");
+  const float* es = reinterpret_cast<const float*>(smem + OFF_KEEP + 4096);
+  float* re_keep = reinterpret_cast<float*>(smem + OFF_KEEP + 12288);   // real part of the sample (result of the first pass), [1680]
+  for (int i = tid; i < 2 * 16 * 8; i += kThreads) {   // 16-byte units of the W2 image: [chunk][row 0..15][unit]
+    const int c = i >> 7, r = (i >> 3) & 15, u = i & 7;
+    uint4 pk = make_uint4(0, 0, 0, 0);
+    if (r < kPatchLen) {
+      const float* w = p.l2_w + r * kD + c * 64 + u * 8;
+      pk = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
+    }
+    *reinterpret_cast<uint4*>(smem + OFF_KEEP + c * 2048 + r * 128 + ((u ^ (r & 7)) << 4)) = pk;
+  }
+  float l2b[kPatchLen];
+#pragma unroll
+  for (int f = 0; f < kPatchLen; ++f) l2b[f] = p.l2_b[f];
+  fence_proxy_async_smem();
+  __syncthreads();
+  uint32_t n_run = 0;
+  constexpr uint32_t kIdescL2 = make_idesc_bf16(128, 16, false, false);
+
+  for (int64_t sample = blockIdx.x; sample < nsamples; sample += gridDim.x) {
+    for (int part = 0; part < 2; ++part, ++n_run) {
+      const int64_t seq = 2 * sample + part;
+      const uint8_t* hs = himg + seq * (int64_t)kXImageBytes;   // encoder output: bf16 operand image (tc_layout.cuh)
+#ifdef AFT_TC_TIMELINE
+      const bool st_on = blockIdx.x == 0 && n_run == 2 && tid == 0;
+      if (st_on) g_conv_tl[20] = clock64();
+#endif
+      if (warp == 0) {
+        const bool el = elect_one();
+        if (el) {
+          // (the previous part ended with a __syncthreads: nobody reads the mid planes or the enhanced image any more)
+          mbar_arrive_expect_tx(bar + 32, kXImageBytes + kPix * sizeof(float));
+          bulk_g2s(sb + kImgOff, hs, kXImageBytes, bar + 32);
+          bulk_g2s(sb + OFF_KEEP + 4096, enh + seq * (int64_t)kPix, kPix * sizeof(float), bar + 32);
+          // the next part's inputs travel HBM -> L2 while this part's conv stack runs
+          const int64_t nseq2 = part == 0 ? seq + 1 : 2 * (sample + gridDim.x);
+          if (nseq2 < 2 * nsamples) {
+            bulk_prefetch_l2(himg + nseq2 * (int64_t)kXImageBytes, kXImageBytes);
+            bulk_prefetch_l2(enh + nseq2 * (int64_t)kPix, kPix * sizeof(float));
+          }
+        }
+        mbar_wait(bar + 32, n_run & 1);
+        tc_fence_after_sync();
+        constexpr uint32_t kHi = (uint32_t)(desc_k_sw128_const() >> 32);
+        const uint32_t lo = (uint32_t)desc_k_sw128_const();
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t a = lo | (((sb + kImgOff + c * kXChunkBytes + t * 128 * 128) >> 4) & 0x3FFF);
+              const uint32_t b = lo | (((sb + OFF_KEEP + c * 2048) >> 4) & 0x3FFF);
+              mma_ss(tmem + t * 16, ((uint64_t)kHi << 32) | (a + ks * 2), ((uint64_t)kHi << 32) | (b + ks * 2), kIdescL2, (c | ks) != 0, el);
+            }
+        mma_commit(bar + 40, el);
+      }
+      mbar_wait(bar + 32, n_run & 1);   // the enhanced image is read with generic loads below
+      mbar_wait(bar + 40, n_run & 1);
+      tc_fence_after_sync();
+      // linear_2 epilogue (encoders.py:70), Fold (patch_processors.py:69-71) and the residual (fortitran.py:228): one
+      // thread per token (warps 0..11: row tile warp / 4, lane quadrant warp % 4)
+      if (warp < 12) {
+        const int t = (warp >> 2) * 128 + (warp & 3) * 32 + (tid & 31);
+        uint32_t acc[8];
+        tmem_ld8p(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 16, acc);
+        tmem_wait_ld();
+        if (t < kS) {
+          const int pi = t / kTokW, pj = t - pi * kTokW;
+#pragma unroll
+          for (int f = 0; f < kPatchLen; ++f) {
+            const int a = f / kPatchW, b = f - a * kPatchW;
+            const int r = kPatchH * pi + a, c = kPatchW * pj + b;
+            in[(r + 1) * kPW + c + 1] = __uint_as_float(acc[f]) + l2b[f] + es[r * kGridW + c];
+          }
+        }
+      }
+      // the staged image overwrote the zero guards between mid groups 1 | 2 and 2 | 3: the conv stack reads them as padding
+      for (int i = tid; i < 2 * 64; i += kThreads) {
+        const int g = i >> 6;   // boundary between groups g + 1 and g + 2: back guard of the first + front guard of the second = 1024 bytes
+        *reinterpret_cast<uint4*>(smem + OFF_MID + (g + 2) * kPlaneBytes - kPosGuard * 16 + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
+      }
+      tc_fence_before_sync();
+      __syncthreads();
+#else
   // Input staging of one part: the encoder's output image (72 KB) goes into the position areas of mid groups 1..3 (dead
   // between two stack runs; the guards between the groups stay zero), the enhanced image (fp32, 6.7 KB) behind the
   // linear_2 weights in the persistent scratch.  Both arrive by bulk copies on the mbarrier at bar + 32.
@@ -261,6 +388,7 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
         }
       }
       __syncthreads();
+#endif
 #ifdef AFT_TC_TIMELINE
       if (st_on) g_conv_tl[21] = clock64();
 #endif
@@ -336,15 +464,22 @@ bool conv_tc_pack(const ConvPack& src, void* dst, cudaStream_t st) {
 }
 
 bool launch_frontend_tc(const FrontPack& p, const void* pack, const float2* pilots, const float* snr, const float* ds,
-                        const float* dop, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st) {
+                        const float* dop, float* zbuf, float* enh, __nv_bfloat16* hb, int64_t nsamples, int sm_count, cudaStream_t st) {
   if (cudaFuncSetAttribute(frontend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStackSmemBytes) != cudaSuccess) {
     set_error("frontend_tc: cannot opt in to %d bytes of shared memory: %s", kStackSmemBytes, cudaGetErrorString(cudaGetLastError()));
     return false;
   }
   if (nsamples <= 0) return true;
   const int64_t nseq = 2 * nsamples;
+  if (p.adaptive) {
+    if (p.h1 > kMaxAdaHidden || p.h2 > kMaxAdaHidden) { set_error("adapter hidden sizes exceed %d", kMaxAdaHidden); return false; }
+    const int64_t groups = (nsamples + kAdaGroup - 1) / kAdaGroup;
+    adapter_kernel<<<(unsigned)(groups < sm_count ? groups : sm_count), kAdaThreads, 0, st>>>(p, snr, ds, dop, zbuf, nsamples);
+    count_launch();
+    if (!check_launch("adapter_kernel")) return false;
+  }
   frontend_tc_kernel<<<(unsigned)(nseq < sm_count ? nseq : sm_count), kThreads, kStackSmemBytes, st>>>(
-      p, static_cast<const uint8_t*>(pack), pilots, snr, ds, dop, enh, hb, nseq);
+      p, static_cast<const uint8_t*>(pack), pilots, zbuf, enh, hb, nseq);
   count_launch();
   return check_launch("frontend_tc_kernel");
 }

@@ -115,7 +115,8 @@ enum : uint32_t {
   MB_P_READY = 120,    // warp  : P tile written to TMEM
   MB_PV_DONE = 128,    // commit: P.V complete (P columns free, O accumulator valid)
   MB_O_FREE = 136,     // 2 x warp : O accumulator buffer b read out, O image columns written
-                       // (152, 160, 224: free -- the per-tile OUT_DONE / X1_READY / X2_READY barriers live in the second block)
+  MB_TAIL_MAX = 152,   // warp  : sliced tail, partial row maxima of every compute warp published
+                       // (160, 224: free -- the per-tile OUT_DONE / X1_READY / X2_READY barriers live in the second block)
   MB_F1_DONE = 168,    // commit: FFN1 accumulator tile (128 rows x 128 hidden units) complete
   MB_F1_FREE = 176,    // warp  : FFN1 accumulator tile read out
   MB_F2_DONE = 184,    // 3 x commit: FFN2 partial product of row tile t complete (hidden rows of the tile free / final result)
@@ -609,9 +610,8 @@ __device__ __forceinline__ void epi_o_tail(uint32_t tmem, uint32_t sb, int g, in
 // sums through the ordinary exchange arrays, each thread using the slot it also owns in the full tiles ([part][32 q +
 // lane]): a warp only overwrites slots of its own quadrant, whose previous readers (the quadrant's warps, second named
 // barrier of tile 1) are behind it, and the next full-tile writers are a whole QKV hand-shake away.
-constexpr int kTailBar = 11;   // named barrier of all compute warps: tail maxima exchanged
 template <int NC>
-__device__ __forceinline__ void softmax_tail_sliced_impl(uint32_t tmem, uint32_t sb, uint32_t miscb, uint32_t s_loaded_bar, int q, int part, int lane) {
+__device__ __forceinline__ void softmax_tail_sliced_impl(uint32_t tmem, uint32_t sb, uint32_t miscb, uint32_t s_loaded_bar, uint32_t tail_bar, uint32_t tail_parity, int q, int part, int lane) {
   static_assert(NC % 8 == 0, "a thread's keys must be whole 16-byte units of the P image");
   const int key0 = tail_key0(q) + part * NC;
   float v[NC];
@@ -634,7 +634,12 @@ __device__ __forceinline__ void softmax_tail_sliced_impl(uint32_t tmem, uint32_t
   st_shared_f32(miscb + MISC_XMAX + own, m);
   tc_fence_before_sync();
   warp_arrive(s_loaded_bar, lane);
-  named_bar_sync(kTailBar, 32 * kComputeWarps);
+  // rendezvous of all compute warps (the 16 partial maxima of every row are published): an mbarrier rather than a named
+  // barrier -- the two instantiations of this function are different call sites, which compute-sanitizer's synccheck
+  // reports for bar.sync; sharing one call site instead cost 4 % of the kernel (the score registers had to survive a
+  // merge of the two branches)
+  warp_arrive(tail_bar, lane);
+  mbar_wait(tail_bar, tail_parity);
 #pragma unroll
   for (int pp = 0; pp < 4; ++pp)
 #pragma unroll
@@ -667,10 +672,11 @@ __device__ __forceinline__ void softmax_tail_sliced_impl(uint32_t tmem, uint32_t
   unpack2(s2, sa, sb2);
   st_shared_f32(miscb + MISC_XSUM + own, sa + sb2);
 }
-__device__ __forceinline__ void softmax_tail_sliced(uint32_t tmem, uint32_t sb, uint32_t miscb, uint32_t s_loaded_bar, int q, int part, int lane) {
+__device__ __forceinline__ void softmax_tail_sliced(uint32_t tmem, uint32_t sb, uint32_t miscb, uint32_t s_loaded_bar, uint32_t tail_bar,
+                                                    uint32_t tail_parity, int q, int part, int lane) {
   static_assert(kParts == 4 || AFT_TC_TAILT != 2, "the sliced tail assumes four warpgroups");
-  if (q == 0) softmax_tail_sliced_impl<24>(tmem, sb, miscb, s_loaded_bar, q, part, lane);
-  else softmax_tail_sliced_impl<16>(tmem, sb, miscb, s_loaded_bar, q, part, lane);
+  if (q == 0) softmax_tail_sliced_impl<24>(tmem, sb, miscb, s_loaded_bar, tail_bar, tail_parity, q, part, lane);
+  else softmax_tail_sliced_impl<16>(tmem, sb, miscb, s_loaded_bar, tail_bar, tail_parity, q, part, lane);
 }
 // O_tail accumulator (M = 64: tail query i in lane i % 16 of quadrant i / 16) -> / l -> bf16 -> O image rows 256..279
 __device__ __forceinline__ void epi_o_tail_sliced(uint32_t tmem, uint32_t sb, uint32_t miscb, int g, int obuf, int q, int part, int lane) {
@@ -974,7 +980,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
                                     MB_W_EMPTY, MB_W_EMPTY + 8, MB_W_EMPTY + 16, MB_W_EMPTY + 24, MB_QKV_DONE, MB_S_DONE,
                                     MB_PV_DONE, MB_F1_DONE, MB_F2_DONE, MB_F2_DONE + 8, MB_F2_DONE + 16};
     const uint32_t warp_bars[] = {MB_X_FREE, MB_QKV_READY, MB_S_LOADED, MB_P_READY, MB_O_FREE, MB_O_FREE + 8,
-                                  MB_F1_FREE, MB_HID_READY, MB_HID_READY + 8};
+                                  MB_F1_FREE, MB_HID_READY, MB_HID_READY + 8, MB_TAIL_MAX};
     for (uint32_t b : commit_bars) mbar_init(misc + b, 1);
     for (uint32_t b : warp_bars) mbar_init(misc + b, kComputeWarps);
     for (uint32_t t = 0; t < 3; ++t) {
@@ -1336,7 +1342,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encoder_kernel(EncParams p) {
               tc_fence_after_sync();
               tl_event(p, tl, 232, tl_n);       // S^T seen
 #if AFT_TC_TAILT == 2
-              softmax_tail_sliced(tmem, sb, miscb, misc + MB_S_LOADED, q, part, lane);
+              softmax_tail_sliced(tmem, sb, miscb, misc + MB_S_LOADED, misc + MB_TAIL_MAX, n_head & 1, q, part, lane);
 #else
               softmax_tail(tmem, sb, misc + MB_S_LOADED, q, part, lane);
 #endif
@@ -1658,7 +1664,8 @@ size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 size_t tc_workspace_bytes(int64_t bc) {
   const size_t nseq = 2 * (size_t)bc;
-  return align_up_sz(nseq * kPix * sizeof(float), 1024) + align_up_sz(nseq * (size_t)kXImageBytes, 1024);
+  return align_up_sz(nseq * kPix * sizeof(float), 1024) + align_up_sz(nseq * (size_t)kXImageBytes, 1024) +
+         align_up_sz((size_t)bc * 3 * 2 * kS * sizeof(float), 1024);   // enhanced images | X images | adaptive features
 }
 
 bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack& head, int activation, int sm_count,
@@ -1669,8 +1676,9 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   char* ws = static_cast<char*>(workspace);
   float* enh = reinterpret_cast<float*>(ws);
   char* ximg = ws + align_up_sz(nseq * kPix * sizeof(float), 1024);
+  float* zbuf = reinterpret_cast<float*>(ximg + align_up_sz(nseq * (size_t)kXImageBytes, 1024));
   mark();
-  if (!launch_frontend_tc(front, w.conv_front, pilots, snr, ds, dop, enh, reinterpret_cast<__nv_bfloat16*>(ximg), nsamples, sm_count, st)) return false;
+  if (!launch_frontend_tc(front, w.conv_front, pilots, snr, ds, dop, zbuf, enh, reinterpret_cast<__nv_bfloat16*>(ximg), nsamples, sm_count, st)) return false;
   if (cudaFuncSetAttribute(encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes) != cudaSuccess) {
     set_error("encoder_kernel: cannot opt in to %u bytes of shared memory: %s", kTcSmemBytes, cudaGetErrorString(cudaGetLastError()));
     return false;
@@ -1823,6 +1831,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_tail_kernel(const char
   if (threadIdx.x == 0) {
     mbar_init(misc + MB_X_FULL, 1); mbar_init(misc + MB_S_DONE, 1); mbar_init(misc + MB_PV_DONE, 1);
     mbar_init(misc + MB_P_READY, kComputeWarps); mbar_init(misc + MB_S_LOADED, kComputeWarps);
+    mbar_init(misc + MB_TAIL_MAX, kComputeWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(miscb + MISC_TMEM_PTR, 512); tmem_relinquish(); }
@@ -1859,7 +1868,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) selftest_tail_kernel(const char
         tmem_wait_ld();
         for (int j = 0; j < 8; ++j) s_out[(key0 + c0 + j) * 32 + lane] = __uint_as_float(x[j]);
       }
-      softmax_tail_sliced(tmem, sb, miscb, misc + MB_S_LOADED, q, part, lane);
+      softmax_tail_sliced(tmem, sb, miscb, misc + MB_S_LOADED, misc + MB_TAIL_MAX, 0, q, part, lane);
     } else {
       for (int b = 0; b < (q == 0 ? 3 : 2); ++b) {   // raw scores
         uint32_t x[kTq];

@@ -396,6 +396,9 @@ enum : uint32_t {
 constexpr uint32_t ATM_S = 0, ATM_P = 128, ATM_O = 192;
 constexpr uint32_t kIdS = make_idesc_bf16(128, 128, false, false), kIdPV = make_idesc_bf16(128, 32, false, true);
 constexpr int kAtRegsCompute = 208, kAtRegsCtrl = 40;
+#ifndef AFT_LONG_POLY
+#define AFT_LONG_POLY 8     // N > 0: one pair of exponentials in N runs on the FMA pipe (packed Cody-Waite + cubic, tc_math.cuh)
+#endif
 
 __global__ void __launch_bounds__(kAtThreads, 2) attn_long_kernel(AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -525,9 +528,15 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_long_kernel(AttnParams p) 
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int c = i * 16 + 2 * jj;
-          float a, b;
-          unpack2(add2(pack2(v[c], v[c + 1]), negm2), a, b);
-          const f32x2 e2 = pack2(ex2(a), ex2(b));
+          const f32x2 x2 = add2(pack2(v[c], v[c + 1]), negm2);
+          f32x2 e2;
+          if (AFT_LONG_POLY > 0 && jj % (AFT_LONG_POLY > 0 ? AFT_LONG_POLY : 1) == (AFT_LONG_POLY > 0 ? AFT_LONG_POLY : 1) - 1) {
+            e2 = ex2_poly2(x2);   // a share of the exponentials on the FMA pipe: the loop is MUFU-bound otherwise
+          } else {
+            float a, b;
+            unpack2(x2, a, b);
+            e2 = pack2(ex2(a), ex2(b));
+          }
           if (jj & 1) s2b = add2(s2b, e2); else s2a = add2(s2a, e2);
           pk[jj] = pack_bf16_pair(e2);
         }

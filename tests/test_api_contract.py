@@ -28,6 +28,17 @@ def test_reference_import_paths():
     from src.config.schemas import ModelConfig as MC, SystemConfig as SC  # noqa: F401
     from src.models import AdaFortiTranEstimator as A, FortiTranEstimator as F
     assert A is AdaFortiTranEstimator and F is FortiTranEstimator
+    # the evaluation half of the reference tree (trainer.py:259-347 and what it imports)
+    from src.config.config_loader import ConfigLoader, load_config as lc2   # noqa: F401
+    from src.data import MatDataset, get_test_dataloaders                    # noqa: F401
+    from src.main.trainer import MODEL_REGISTRY, ModelEvaluator               # noqa: F401
+    from src.models.adafortitran import AdaFortiTranEstimator as A2
+    from src.models.fortitran import BaseFortiTranEstimator, FortiTranEstimator as F2   # noqa: F401
+    from src.models.linear import LinearEstimator                             # noqa: F401
+    from src.utils import concat_complex_channel, extract_values, mse, to_db   # noqa: F401
+    assert A2 is A and F2 is F and MODEL_REGISTRY["adafortitran"] is A
+    x = torch.complex(torch.arange(6.).reshape(1, 2, 3), -torch.arange(6.).reshape(1, 2, 3))
+    assert torch.equal(concat_complex_channel(x), torch.cat((x.real, x.imag), dim=1)) and abs(to_db(100.0) - 20.0) < 1e-12
 
 
 def test_schema_validation_errors(tmp_path):
@@ -106,6 +117,51 @@ def test_forward_errors_without_gpu_path():
     a.train()
     with pytest.raises(RuntimeError, match="inference-only"):
         a(x, util.meta([0, 0], [50, 50], [200, 200]))
+
+
+def test_forward_host_validates_like_forward():
+    """forward_host used to skip the argument checks: a wrong pilot shape / meta length / output buffer must be a
+    Python error, never an out-of-bounds host read or write inside the library."""
+    a = util.make_model("ada", device="cpu")
+    md = util.meta([0, 0], [50, 50], [200, 200])
+    with pytest.raises(ValueError, match="meta_data is required"):
+        a.forward_host(torch.zeros(2, 12, 2, dtype=torch.cfloat))
+    with pytest.raises(ValueError, match="expected pilot_symbols of shape"):
+        a.forward_host(torch.zeros(2, 11, 2, dtype=torch.cfloat), md)
+    with pytest.raises(TypeError, match="complex"):
+        a.forward_host(torch.zeros(2, 12, 2), md)
+    with pytest.raises(ValueError, match="must have 2 elements"):
+        a.forward_host(torch.zeros(2, 12, 2, dtype=torch.cfloat), util.meta([0] * 3, [50] * 3, [200] * 3))
+    for bad in (torch.zeros(1, 120, 14, dtype=torch.cfloat), torch.zeros(2, 120, 14), torch.zeros(2, 14, 120, dtype=torch.cfloat).transpose(1, 2)):
+        with pytest.raises(ValueError, match="out must be a contiguous CPU complex64"):
+            a.forward_host(torch.zeros(2, 12, 2, dtype=torch.cfloat), md, out=bad)
+    a.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        a.forward_host(torch.zeros(2, 12, 2, dtype=torch.cfloat), md)
+
+
+def test_weight_staleness_controls():
+    a = util.make_model("forti", device="cpu")
+    a._packed_key = ("something",)
+    a.invalidate_weights()
+    assert a._packed_key is None
+    a._packed_key = ("something",)
+    a.load_state_dict(a.state_dict())          # load_state_dict always forces a repack
+    assert a._packed_key is None
+    a.weight_check = "bogus"
+    with pytest.raises(ValueError, match="weight_check"):
+        a._sync_weights()
+
+
+def test_linear_estimator_follows_its_parameters():
+    from adafortitran_b200 import LinearEstimator, ModelConfig, SystemConfig
+    m = LinearEstimator(SystemConfig(**util.SYS), ModelConfig(**dict(util.FORTI, model_type="linear", device="cpu"))).eval()
+    assert m.device.type == "cpu"
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        with torch.no_grad():
+            m(torch.zeros(2, 12, 2))
+    m.to(torch.float64)                          # _apply keeps .device in sync with the parameters
+    assert m.device == m.linear.weight.device
 
 
 def test_patch_maps_match_oracle():

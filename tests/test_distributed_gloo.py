@@ -38,6 +38,31 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_ragged(rank, world, port, q):
+    """Unequal shards (7 samples over 2 ranks): gather_estimates pads for the collective and trims afterwards."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(9)
+        full = torch.view_as_complex(torch.randn(7, 12, 4, 2, generator=g))
+        lo, hi = D.shard_range(7, rank, world)
+        gathered = D.gather_estimates(full[lo:hi].clone())
+        q.put((rank, bool(torch.equal(gathered, full)), tuple(gathered.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_unequal_shards_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ragged, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    results = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert all(r[1] and r[2] == (7, 12, 4) for r in results), results
+
+
 def test_shard_range_partitions_exactly():
     for batch in (0, 1, 7, 64, 65536):
         for world in (1, 2, 3, 8):

@@ -102,6 +102,43 @@ def test_sweep_delta_nmse(sd):
     assert worst <= 0.05, worst
 
 
+def test_trained_weights_sweep():
+    """The accuracy gates on weights that MEAN something: a pseudo-trained AdaFortiTran (a few hundred Adam steps of the live
+    reference on synthetic channels, tests/golden/make_golden_trained.py; NMSE -3 ... -13 dB per condition instead of the
+    ~0 dB of a random initialisation).  Per condition of the 21-point sweep: the fp32 path reproduces the reference's
+    recorded outputs (<= 1e-4 normwise), and the bf16 path keeps the reference's NMSE within the north-star's 0.05 dB and
+    its output within -30 dB of output-relative error power."""
+    g = util.golden("golden_trained.npz")
+    sd = {k[3:]: g[k] for k in g if k.startswith("sd/")}
+    m32 = util.make_model("ada", weights=sd, precision="fp32")
+    mbf = util.make_model("ada", weights=sd, precision="bf16")
+    n, seed0 = int(g["samples"]), int(g["seed0"])
+    rows, worst_d, worst_rel, worst_32 = [], 0.0, -1e9, 0.0
+    for i, (snr, ds, dop) in enumerate(g["conds"]):
+        pilots, truth = O.synthetic_channel(int(g["gen_batch"]), float(snr), float(ds), float(dop), seed=seed0 + i)   # as the generator drew them
+        pilots, truth = pilots[:n], truth[:n]
+        args = (pilots, np.full(n, snr, np.float32), np.full(n, ds, np.float32), np.full(n, dop, np.float32))
+        ref = g["out"][i]
+        assert abs(O.nmse_db(ref, truth) - float(g["nmse_db"][i])) < 1e-3        # inputs regenerated exactly
+        y32, ybf = run(m32, *args), run(mbf, *args)
+        e32 = O.normwise_err(y32, ref)
+        d = abs(O.nmse_db(ybf, truth) - O.nmse_db(ref, truth))
+        rel = O.rel_err_db(ybf, ref)
+        worst_d, worst_rel, worst_32 = max(worst_d, d), max(worst_rel, rel), max(worst_32, e32)
+        rows.append(dict(snr=float(snr), ds=float(ds), doppler=float(dop), nmse_ref_db=O.nmse_db(ref, truth),
+                         nmse_fp32_db=O.nmse_db(y32, truth), nmse_bf16_db=O.nmse_db(ybf, truth), fp32_normwise=e32, bf16_rel_err_db=rel))
+    import json, os
+    out = os.path.join(util.ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "trained_sweep_bf16_vs_reference.json"), "w") as f:
+        json.dump(dict(worst_abs_delta_nmse_db=worst_d, worst_bf16_rel_err_db=worst_rel, worst_fp32_normwise=worst_32,
+                       conditions=rows), f, indent=1)
+    assert max(r["nmse_ref_db"] for r in rows) < -2.5          # the fixture is informative: every condition well below 0 dB
+    assert worst_32 <= 1e-4, worst_32
+    assert worst_d <= 0.05, worst_d
+    assert worst_rel <= -30.0, worst_rel
+
+
 def test_ragged_and_chunked_batches(sd):
     """Batch sizes that do not fill the persistent grid (1, 3, 75 = 150 sequences > 148 CTAs) and one that crosses the
     internal chunk boundary (8192 + 3); properties: determinism, permutation equivariance, re/im independence."""

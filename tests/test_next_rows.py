@@ -190,6 +190,10 @@ def test_collate_on_device(tmp_path):
 
 
 # ----------------------------------------------------------------------------------------- N4: evaluator
+EVAL_SETS = {"DS_50": [f"{i}_SNR-20_DS-50_DOP-500_N-3_TDL-A.mat" for i in range(1, 8)],
+             "DS_200": [f"{i}_SNR-10_DS-200_DOP-900_N-3_TDL-B.mat" for i in range(1, 6)]}
+
+
 def _write_test_sets(root, names_by_dir, seed=21):
     import scipy.io as sio
     rng = np.random.default_rng(seed)
@@ -211,8 +215,7 @@ def test_evaluator_matches_reference_formula(tmp_path):
     from adafortitran_b200 import evaluate
     from adafortitran_b200.config import PilotParams
     from oracle.torch_port import TorchPort
-    sets = {"DS_50": [f"{i}_SNR-20_DS-50_DOP-500_N-3_TDL-A.mat" for i in range(1, 8)],
-            "DS_200": [f"{i}_SNR-10_DS-200_DOP-900_N-3_TDL-B.mat" for i in range(1, 6)]}
+    sets = EVAL_SETS
     _write_test_sets(tmp_path, sets)
     sd = util.ada_weights()
     model = util.make_model("ada", weights=sd, precision="fp32")
@@ -220,6 +223,11 @@ def test_evaluator_matches_reference_formula(tmp_path):
     assert sorted(n for n, _ in loaders) == ["DS_200", "DS_50"]
     stats = evaluate.ModelEvaluator(model, model.device).get_test_stats(loaders)
     assert list(stats) == [50, 200]
+    # the reference's OWN ModelEvaluator.get_test_stats on the same files (tests/golden/make_golden_evaluator.py, live reference)
+    ge = util.golden("golden_evaluator.npz")
+    assert int(ge["batch_size"]) == 3 and list(ge["keys"]) == [50, 200]
+    for k, want in zip(ge["keys"], ge["mse_db"]):
+        assert abs(stats[int(k)] - float(want)) <= 2e-3, (k, stats, want)
     # reference side: CPU port of the model + the reference's metric, batch by batch
     port = TorchPort(sd, adaptive=True).eval()
     for sub, names in sets.items():

@@ -86,3 +86,20 @@ def test_metric_definitions():
     cat = lambda z: np.concatenate([z.real, z.imag], axis=1)
     ref = 10 * np.log10(2 * np.mean((cat(a) - cat(b)) ** 2))
     assert abs(O.mse_db_reference(a, b) - ref) < 1e-12
+
+
+def test_oracle_on_trained_weights():
+    """The pseudo-trained fixture (tests/golden/make_golden_trained.py: the live reference after 400 Adam steps): the numpy
+    oracle reproduces the reference's recorded outputs, and the fixture is informative (NMSE well below 0 dB)."""
+    g = util.golden("golden_trained.npz")
+    sd = {k[3:]: g[k] for k in g if k.startswith("sd/")}
+    n = int(g["samples"])
+    assert float(g["nmse_db"].max()) < -2.5 and float(g["nmse_db"].min()) < -10.0
+    for i in (0, 7, 20):
+        s, d, f = (float(v) for v in g["conds"][i])
+        p, h = O.synthetic_channel(int(g["gen_batch"]), s, d, f, seed=int(g["seed0"]) + i)
+        p, h = p[:n], h[:n]
+        y = O.forward(util.oracle_cfg("ada"), sd, p, np.full(n, s, np.float32), np.full(n, d, np.float32), np.full(n, f, np.float32),
+                      dtype=np.float32)
+        assert O.normwise_err(y, g["out"][i]) <= 5e-6
+        assert abs(O.nmse_db(g["out"][i], h) - float(g["nmse_db"][i])) < 1e-3

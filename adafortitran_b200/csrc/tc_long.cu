@@ -9,12 +9,12 @@
 //       [attention output tile] -> out_proj + residual + LayerNorm1 -> linear1 + GELU -> linear2 + residual + LayerNorm2
 //       -> residual tile (bf16, in place)  [-> in_proj of the NEXT layer -> Q / K / V head tiles]
 //     The first launch only runs the in_proj part (layer 0), the last one writes the fp32 rows the head reads.
-//   attn_long_kernel  (one CTA per (sequence, head, 128-query tile), two CTAs per SM):
-//       streaming attention over the 128-key tiles of the head: S = Q K^T (tcgen05, accumulator in TMEM), online softmax
+//   attn_long_kernel  (one CTA per (sequence, head, 128-query tile), four CTAs per SM):
+//       streaming attention over 64-key tiles of the head: S = Q K^T (tcgen05, accumulator in TMEM), online softmax
 //       (running maximum / sum per row, one thread per query row, log2 domain), P (bf16) back to TMEM as the A operand
-//       of P.V, per-tile products accumulated and rescaled in registers.  K / V tiles stream through a 3-stage ring of
-//       1-D bulk copies; the next score tile is issued while the exponentials of the current one run, and the second
-//       CTA of the SM fills the tensor pipe / MUFU bubbles of the first.
+//       of P.V, output accumulator resident in TMEM and rescaled only when a maximum outgrows its reference by 2^8.
+//       K / V tiles stream through a 4-stage ring of 1-D bulk copies; the next score tile is issued while the
+//       exponentials of the current one run, and the other CTAs of the SM fill the tensor pipe / MUFU bubbles.
 //
 // Every operand lives in global memory as a byte-exact image of its shared-memory layout (tc_layout.cuh), per row tile:
 //   residual / attention-output tile : K-major SWIZZLE_128B, 2 chunks x 128 rows x 128 B               = 32,768 B
@@ -381,42 +381,53 @@ __global__ void __launch_bounds__(kLbThreads, 1) lin_block_kernel(LinParams p) {
 // =============================================================================================
 // attn_long_kernel
 // =============================================================================================
+// One CTA = one 128-query tile of one (sequence, head); FOUR CTAs per SM (128 TMEM columns, 41 KB of shared memory and
+// 64 K / 4 registers each), so that sixteen softmax warps per SM are in different phases of their key loops: the loop is
+// bound by the exponentials (MUFU, 16 / clk / SM), and a first version with two CTAs of four warps (one 128-key tile per
+// step, P.V products accumulated in registers) kept the MUFU pipe only 66 % busy.
+//   key tile = 64 keys: S [128 x 64] (2 MMAs) -> one thread per query row: running maximum, exponentials, P (bf16) -> TMEM
+//   -> O += P . V (4 MMAs, accumulator stays in TMEM across the key loop).
+// The accumulator is only rescaled when a row maximum has grown by more than 2^8 since the last rescale (the scores are
+// in log2 units; in between P is computed against the stale maximum, i.e. P <= 256, exact in bf16's exponent range), so
+// the common path has no TMEM round trip of O -- the scheme of FlashAttention-4's correction step.
 struct AttnParams {
   const char *q, *k, *v;   // head tiles
   char* aimg;              // attention output tiles (out_proj operand images)
   int T, S;
 };
 constexpr int kAtThreads = 256;   // warps 0..3: one thread per query row; warp 4: MMA issuer; warp 5: producer; 6, 7 idle
-constexpr int kAtStages = 3;
-constexpr uint32_t AT_Q = 0, AT_KV = 8192, AT_BAR = AT_KV + kAtStages * 16384, kAtSmem = AT_BAR + 256;   // 57,600
+constexpr int kAtStages = 4, kKeyTile = 64;
+constexpr uint32_t kKvStage = 8192;                      // K (4 KB) | V (4 KB) of one 64-key tile
+constexpr uint32_t AT_Q = 0, AT_KV = 8192, AT_BAR = AT_KV + kAtStages * kKvStage, kAtSmem = AT_BAR + 256;   // 41,216
 enum : uint32_t {
-  ATB_Q = 0, ATB_S_DONE = 8, ATB_S_LOADED = 16, ATB_P_READY = 24, ATB_PV_DONE = 32 /* 2 */, ATB_O_FREE = 48 /* 2 */,
-  ATB_KV_FULL = 64 /* 3 */, ATB_KV_EMPTY = 88 /* 3 */, ATB_TMEM = 120
+  ATB_Q = 0, ATB_S_DONE = 8, ATB_S_LOADED = 16, ATB_P_READY = 24, ATB_PV_DONE = 32, ATB_KV_FULL = 40 /* 4 */, ATB_KV_EMPTY = 72 /* 4 */,
+  ATB_TMEM = 112
 };
-constexpr uint32_t ATM_S = 0, ATM_P = 128, ATM_O = 192;
-constexpr uint32_t kIdS = make_idesc_bf16(128, 128, false, false), kIdPV = make_idesc_bf16(128, 32, false, true);
-constexpr int kAtRegsCompute = 208, kAtRegsCtrl = 40;
+constexpr uint32_t ATM_S = 0, ATM_P = 64, ATM_O = 96;
+constexpr uint32_t kIdS = make_idesc_bf16(128, 64, false, false), kIdPV = make_idesc_bf16(128, 32, false, true);
+constexpr int kAtRegsCompute = 104, kAtRegsCtrl = 24;
+constexpr float kRescaleThreshold = 8.0f;
 #ifndef AFT_LONG_POLY
-#define AFT_LONG_POLY 8     // N > 0: one pair of exponentials in N runs on the FMA pipe (packed Cody-Waite + cubic, tc_math.cuh)
+#define AFT_LONG_POLY 4     // N > 0: one pair of exponentials in N runs on the FMA pipe (packed Cody-Waite + cubic, tc_math.cuh)
 #endif
 
-__global__ void __launch_bounds__(kAtThreads, 2) attn_long_kernel(AttnParams p) {
+__global__ void __launch_bounds__(kAtThreads, 4) attn_long_kernel(AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sb = smem_u32(smem_raw);
   if ((sb & 1023u) != 0) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar = sb + AT_BAR;
   const int T = p.T, qt = blockIdx.x, g = blockIdx.y;
+  const int nkt = (p.S + kKeyTile - 1) / kKeyTile;        // 64-key tiles (the last one may be partly padding)
   const int64_t seq = blockIdx.z;
   const int64_t head_base = ((seq * 4 + g) * T) * (int64_t)kHeadTile;
   if (threadIdx.x == 0) {
-    mbar_init(bar + ATB_Q, 1); mbar_init(bar + ATB_S_DONE, 1);
+    mbar_init(bar + ATB_Q, 1); mbar_init(bar + ATB_S_DONE, 1); mbar_init(bar + ATB_PV_DONE, 1);
     mbar_init(bar + ATB_S_LOADED, 4); mbar_init(bar + ATB_P_READY, 4);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar + ATB_PV_DONE + 8 * b, 1); mbar_init(bar + ATB_O_FREE + 8 * b, 4); }
     for (int s = 0; s < kAtStages; ++s) { mbar_init(bar + ATB_KV_FULL + 8 * s, 1); mbar_init(bar + ATB_KV_EMPTY + 8 * s, 1); }
     fence_mbar_init();
   }
-  if (warp == 4) { tmem_alloc(bar + ATB_TMEM, 256); tmem_relinquish(); }
+  if (warp == 4) { tmem_alloc(bar + ATB_TMEM, 128); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -429,19 +440,20 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_long_kernel(AttnParams p) 
       // --------------------------------------------------------------------------------------- producer
       mbar_arrive_expect_tx(bar + ATB_Q, kHeadTile);
       bulk_g2s(sb + AT_Q, p.q + head_base + qt * (int64_t)kHeadTile, kHeadTile, bar + ATB_Q);
-      for (int j = 0; j < T; ++j) {
+      for (int j = 0; j < nkt; ++j) {
         const int s = j % kAtStages;
         if (j >= kAtStages) mbar_wait_relaxed(bar + ATB_KV_EMPTY + 8 * s, ((j / kAtStages) - 1) & 1);
-        mbar_arrive_expect_tx(bar + ATB_KV_FULL + 8 * s, 2 * kHeadTile);
-        bulk_g2s(sb + AT_KV + s * 16384, p.k + head_base + j * (int64_t)kHeadTile, kHeadTile, bar + ATB_KV_FULL + 8 * s);
-        bulk_g2s(sb + AT_KV + s * 16384 + kHeadTile, p.v + head_base + j * (int64_t)kHeadTile, kHeadTile, bar + ATB_KV_FULL + 8 * s);
+        mbar_arrive_expect_tx(bar + ATB_KV_FULL + 8 * s, kKvStage);
+        // 64 keys = half of a 128-row head tile image (rows 64 (j & 1) ...: 4 KB, whole swizzle atoms)
+        bulk_g2s(sb + AT_KV + s * kKvStage, p.k + head_base + j * 4096ll, 4096, bar + ATB_KV_FULL + 8 * s);
+        bulk_g2s(sb + AT_KV + s * kKvStage + 4096, p.v + head_base + j * 4096ll, 4096, bar + ATB_KV_FULL + 8 * s);
       }
     } else if (warp == 4) {
       // --------------------------------------------------------------------------------------- MMA issuer
       const bool el = elect_one();
       const uint32_t qd = dlo_k64(sb + AT_Q);
       auto issue_s = [&](int j) {
-        const uint32_t kd = dlo_k64(sb + AT_KV + (j % kAtStages) * 16384);
+        const uint32_t kd = dlo_k64(sb + AT_KV + (j % kAtStages) * kKvStage);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) mma_ss(tmem + ATM_S, d64(qd + ks * 2), d64(kd + ks * 2), kIdS, ks > 0, el);
         mma_commit(bar + ATB_S_DONE, el);
@@ -450,20 +462,19 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_long_kernel(AttnParams p) 
       mbar_wait(bar + ATB_KV_FULL, 0);
       tc_fence_after_sync();
       issue_s(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) {
+      for (int j = 0; j < nkt; ++j) {
+        if (j + 1 < nkt) {
           mbar_wait(bar + ATB_KV_FULL + 8 * ((j + 1) % kAtStages), ((j + 1) / kAtStages) & 1);
           mbar_wait(bar + ATB_S_LOADED, j & 1);          // score tile j is in registers
           tc_fence_after_sync();
           issue_s(j + 1);
         }
-        mbar_wait(bar + ATB_P_READY, j & 1);
-        if (j >= 2) mbar_wait(bar + ATB_O_FREE + 8 * (j & 1), ((j >> 1) - 1) & 1);
+        mbar_wait(bar + ATB_P_READY, j & 1);             // P(j) in TMEM, accumulator rescaled if it had to be
         tc_fence_after_sync();
-        const uint32_t vd = dlo_mn64(sb + AT_KV + (j % kAtStages) * 16384 + kHeadTile);
+        const uint32_t vd = dlo_mn64(sb + AT_KV + (j % kAtStages) * kKvStage + 4096);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) mma_ts(tmem + ATM_O + (j & 1) * 32, tmem + ATM_P + ks * 8, d64(vd + ks * 64), kIdPV, ks > 0, el);
-        mma_commit(bar + ATB_PV_DONE + 8 * (j & 1), el);
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tmem + ATM_O, tmem + ATM_P + ks * 8, d64(vd + ks * 64), kIdPV, j > 0 || ks > 0, el);
+        mma_commit(bar + ATB_PV_DONE, el);
         mma_commit(bar + ATB_KV_EMPTY + 8 * (j % kAtStages), el);
       }
     }
@@ -472,58 +483,62 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_long_kernel(AttnParams p) 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kAtRegsCompute));
     const int rt = warp * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    float m = -INFINITY, l = 0.f;
-    f32x2 o[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = pack2(0.f, 0.f);
-    auto add_tile = [&](int b) {   // o += P.V product of one key tile (accumulator buffer b)
-      uint32_t a[32];
-      tmem_ld_cols(lane_base + ATM_O + b * 32, a);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = add2(o[i], pack2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])));
-    };
+    float m_ref = -INFINITY;   // maximum the accumulator and the row sum are currently scaled to
+    float l = 0.f;
 #pragma unroll 1
-    for (int j = 0; j < T; ++j) {
+    for (int j = 0; j < nkt; ++j) {
       mbar_wait(bar + ATB_S_DONE, j & 1);
       tc_fence_after_sync();
-      float v[128];
+      float v[kKeyTile];
       {
-        uint32_t x[128];
+        uint32_t x[kKeyTile];
         tmem_ld_cols(lane_base + ATM_S, x);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 128; ++c) v[c] = __uint_as_float(x[c]);
+        for (int c = 0; c < kKeyTile; ++c) v[c] = __uint_as_float(x[c]);
       }
       tc_fence_before_sync();
       warp_arrive(bar + ATB_S_LOADED, lane);
-      if (j == T - 1) {   // keys past the sequence are padding
-        const int nvalid = p.S - j * 128;
+      if (j == nkt - 1) {   // keys past the sequence are padding
+        const int nvalid = p.S - j * kKeyTile;
 #pragma unroll
-        for (int c = 0; c < 128; ++c)
+        for (int c = 0; c < kKeyTile; ++c)
           if (c >= nvalid) v[c] = -INFINITY;
       }
       float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-      for (int c = 4; c < 128; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
-      const float mn = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      const float alpha = ex2(m - mn);   // first tile: exp2(-inf) = 0
-      m = mn;
-      if (j > 0) {   // P.V of the previous tile (still in the old scale), then everything moves to the new maximum
-        mbar_wait(bar + ATB_PV_DONE + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+      for (int c = 4; c < kKeyTile; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
+      const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      // P.V(j-1) must be complete before P is overwritten (and before the accumulator may be touched)
+      if (j > 0) {
+        mbar_wait(bar + ATB_PV_DONE, (j - 1) & 1);
         tc_fence_after_sync();
-        add_tile((j - 1) & 1);
-        tc_fence_before_sync();
-        warp_arrive(bar + ATB_O_FREE + 8 * ((j - 1) & 1), lane);
       }
-      const f32x2 al2 = pack2(alpha, alpha);
+      // rescale (whole warp, per-row factors) only when some row's maximum outgrew its reference by more than the threshold
+      const bool grow = mt > m_ref + kRescaleThreshold;
+      if (__any_sync(0xFFFFFFFFu, grow)) {
+        const float mn = fmaxf(m_ref, mt);
+        const float f = ex2(m_ref - mn);   // first tile: exp2(-inf) = 0, the accumulator is not read (j == 0)
+        if (j > 0) {
+          uint32_t a[32];
+          tmem_ld_cols(lane_base + ATM_O, a);
+          tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = mul2(o[i], al2);
-      // exponentials -> P (bf16 pairs) -> TMEM; P.V(j-1) has consumed the previous P (waited for above)
-      const f32x2 negm2 = pack2(-mn, -mn);
+          for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) * f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t (&a8)[8] = *reinterpret_cast<const uint32_t (*)[8]>(a + 8 * i);
+            tmem_st8(lane_base + ATM_O + i * 8, a8);
+          }
+        }
+        l *= f;
+        m_ref = mn;
+      }
+      // exponentials against the reference maximum -> P (bf16 pairs) -> TMEM
+      const f32x2 negm2 = pack2(-m_ref, -m_ref);
       f32x2 s2a = pack2(0.f, 0.f), s2b = pack2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kKeyTile / 16; ++i) {
         uint32_t pk[8];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
@@ -531,7 +546,7 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_long_kernel(AttnParams p) 
           const f32x2 x2 = add2(pack2(v[c], v[c + 1]), negm2);
           f32x2 e2;
           if (AFT_LONG_POLY > 0 && jj % (AFT_LONG_POLY > 0 ? AFT_LONG_POLY : 1) == (AFT_LONG_POLY > 0 ? AFT_LONG_POLY : 1) - 1) {
-            e2 = ex2_poly2(x2);   // a share of the exponentials on the FMA pipe: the loop is MUFU-bound otherwise
+            e2 = ex2_poly2(x2);   // a share of the exponentials on the FMA pipe
           } else {
             float a, b;
             unpack2(x2, a, b);
@@ -546,27 +561,27 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_long_kernel(AttnParams p) 
       float sa, sb2, sc, sd;
       unpack2(s2a, sa, sb2);
       unpack2(s2b, sc, sd);
-      l = fmaf(l, alpha, (sa + sb2) + (sc + sd));
+      l += (sa + sb2) + (sc + sd);
       tc_fence_before_sync();
       warp_arrive(bar + ATB_P_READY, lane);
     }
-    mbar_wait(bar + ATB_PV_DONE + 8 * ((T - 1) & 1), ((T - 1) >> 1) & 1);
+    mbar_wait(bar + ATB_PV_DONE, (nkt - 1) & 1);
     tc_fence_after_sync();
-    add_tile((T - 1) & 1);
+    uint32_t a[32];
+    tmem_ld_cols(lane_base + ATM_O, a);
+    tmem_wait_ld();
     const float inv = 1.0f / l;
     const f32x2 inv2 = pack2(inv, inv);
     char* row = p.aimg + (seq * T + qt) * (int64_t)kTileImg + (g >> 1) * kChunk + rt * 128;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      uint4 pk;
-      pk.x = pack_bf16_pair(mul2(o[4 * u], inv2)); pk.y = pack_bf16_pair(mul2(o[4 * u + 1], inv2));
-      pk.z = pack_bf16_pair(mul2(o[4 * u + 2], inv2)); pk.w = pack_bf16_pair(mul2(o[4 * u + 3], inv2));
-      *reinterpret_cast<uint4*>(row + ((((g & 1) * 4 + u) ^ (rt & 7)) << 4)) = pk;
+      auto sc2 = [&](int i) { return pack_bf16_pair(mul2(pack2(__uint_as_float(a[8 * u + i]), __uint_as_float(a[8 * u + i + 1])), inv2)); };
+      *reinterpret_cast<uint4*>(row + ((((g & 1) * 4 + u) ^ (rt & 7)) << 4)) = make_uint4(sc2(0), sc2(2), sc2(4), sc2(6));
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
+  if (warp == 4) tmem_dealloc(tmem, 128);
 }
 
 size_t align_up_l(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -1668,6 +1668,18 @@ size_t tc_workspace_bytes(int64_t bc) {
          align_up_sz((size_t)bc * 3 * 2 * kS * sizeof(float), 1024);   // enhanced images | X images | adaptive features
 }
 
+// AFT_ENCODER=2|3 selects the encoder kernel (experiments / A-B runs); the default is compiled in
+#ifndef AFT_ENCODER_DEFAULT
+#define AFT_ENCODER_DEFAULT 2
+#endif
+static int encoder_version() {
+  static const int v = [] {
+    const char* e = getenv("AFT_ENCODER");
+    return e && (e[0] == '2' || e[0] == '3') ? e[0] - '0' : AFT_ENCODER_DEFAULT;
+  }();
+  return v;
+}
+
 bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack& head, int activation, int sm_count,
                       const float2* pilots, const float* snr, const float* ds, const float* dop, const OutDst& out,
                       int64_t nsamples, void* workspace, cudaStream_t st, TcProfileHook hook) {
@@ -1692,9 +1704,13 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   ep.timeline = g_timeline_arm;
   const unsigned grid = (unsigned)(nseq < sm_count ? nseq : sm_count);
   mark();
-  encoder_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(ep);
-  count_launch();
-  if (!check_launch("encoder_kernel")) return false;
+  if (encoder_version() == 3) {
+    if (!tc_encoder3_launch(ximg, w.layers_dev, w.num_layers, activation, nseq, sm_count, st)) return false;
+  } else {
+    encoder_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(ep);
+    count_launch();
+    if (!check_launch("encoder_kernel")) return false;
+  }
   mark();
   const bool ok = launch_head_tc(head, w.conv_head, ximg, enh, out, nsamples, sm_count, st);
   mark();

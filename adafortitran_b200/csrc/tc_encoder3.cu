@@ -28,7 +28,7 @@
 // Shared memory map: identical to tc_encoder.cu (O | X | QKV / weight ring | W | MISC); stream t's hidden buffers are the
 // rows of ITS tile inside the two chunks of the O image (dead once out_proj of the tile has completed).
 // Tensor memory: stream s owns columns [160 s, 160 s + 160):  S0 [0,64) S1 [64,128) O [128,160)  |  QKV accumulators
-// [0,96)  |  out_proj / FFN2 accumulator [0,128), FFN1 chunk [128,160).
+// [32,128)  |  out_proj / FFN2 accumulator [0,128), FFN1 chunk [128,160).
 #include <cstdio>
 #include <cstdlib>
 
@@ -44,8 +44,8 @@ namespace {
 using namespace ptx;
 using namespace tcm;
 
-#ifndef AFT_V3_POLY
-#define AFT_V3_POLY 4       // N > 0: one pair of exponentials in N on the FMA pipe (packed Cody-Waite + cubic), the rest on the MUFU
+#ifndef AFT_V3_POLY_MASK
+#define AFT_V3_POLY_MASK 0x88   // bit jj set: pair jj of every 8 pairs of exponentials runs on the FMA pipe (packed Cody-Waite + cubic), the rest on the MUFU
 #endif
 
 constexpr int kThreads3 = 512;
@@ -114,12 +114,22 @@ __device__ __forceinline__ void tmem_st8p(uint32_t taddr, const uint32_t* r) {
 }
 
 struct Enc3Params {
+  unsigned long long* timeline;   // -DAFT_V3_TIMELINE builds: [3][256] (id << 48 | clock) records of block 0 (compute warp 0, compute warp 4, MMA issuer 0)
   char* x_images;
   const TcLayer* layers;
   int num_layers;
   int activation;
   int64_t nseq;
 };
+
+#ifdef AFT_V3_TIMELINE
+#define TL3(slot, id)                                                                                       \
+  do {                                                                                                      \
+    if (tl_on && tl_n < 255) p.timeline[(slot) * 256 + (++tl_n)] = ((unsigned long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFull); \
+  } while (0)
+#else
+#define TL3(slot, id) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // compute-warp epilogues: the thread owns token row r (TMEM lane 32 q + lane of its stream's columns)
@@ -144,37 +154,36 @@ __device__ __forceinline__ void epi_qkv3(uint32_t taddr, uint32_t sb, uint32_t b
     }
 }
 
-// One key tile of the streaming softmax (NC = 64 keys, or the last 32 of which 24 exist): scores -> running maximum ->
-// exponentials against the reference maximum -> P (bf16 pairs) in place -> row sum.  `first`: first key tile of the head.
-// P.V of the previous tile must have completed before the output accumulator is rescaled (rare) and, for the barrier
-// protocol, before this tile's P is announced: the wait sits after the exponentials, where it never blocks.
-template <int NC>
-__device__ __forceinline__ void softmax_tile3(uint32_t s_addr, uint32_t o_addr, bool first, uint32_t pv_bar, uint32_t pv_par, float& m_ref,
-                                              float& lsum) {
-  float v[NC];
-  {
-    uint32_t x[NC];
-    tmem_ld_cols(s_addr, x);
-    tmem_wait_ld();
+// One half tile (32 keys) of the streaming softmax: scores x -> running maximum -> exponentials against the reference maximum
+// -> P (bf16 pairs) in place at p_addr (16 columns) -> row sum.  `first`: first half tile of the head; kMask: the last 32
+// keys of the sequence, of which 24 exist.  The output accumulator is rescaled only when some row's maximum outgrew its
+// reference by 2^8 (rare): P.V of the previous key tile must have completed then (`pv_waited` tells the caller that the
+// wait has happened).
+template <bool kMask, bool kSecond>
+__device__ __forceinline__ void softmax_half3(const uint32_t (&x)[32], uint32_t p_addr, uint32_t o_addr, bool first, bool has_prev_pv,
+                                              uint32_t pv_bar, uint32_t pv_par, bool& pv_waited, float& m_ref, float& lsum, int tok_wait,
+                                              int tok_pass) {
+  float v[32];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) v[c] = __uint_as_float(x[c]);
-  }
-  if (NC == 32) {
+  for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(x[c]);
+  if (kMask) {
 #pragma unroll
     for (int c = kS - 256; c < 32; ++c) v[c] = -INFINITY;   // keys 280..287 are padding
   }
   float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-  for (int c = 4; c < NC; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
+  for (int c = 4; c < 32; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
   const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  bool waited = first;
   if (__any_sync(0xFFFFFFFFu, mt > m_ref + kRescale3)) {
     const float mn = fmaxf(m_ref, mt);
-    const float f = ex2(m_ref - mn);   // first tile: exp2(-inf) = 0
+    const float f = ex2(m_ref - mn);   // first half tile: exp2(-inf) = 0
     if (!first) {
-      mbar_wait(pv_bar, pv_par);
-      tc_fence_after_sync();
-      waited = true;
+      if (has_prev_pv && !pv_waited) {
+        mbar_wait_spin(pv_bar, pv_par);
+        tc_fence_after_sync();
+        pv_waited = true;
+      }
+      // (the P.V of THIS key tile cannot be in flight: it is issued after both halves of P have been announced)
       uint32_t a[32];
       tmem_ld_cols(o_addr, a);
       tmem_wait_ld();
@@ -182,21 +191,38 @@ __device__ __forceinline__ void softmax_tile3(uint32_t s_addr, uint32_t o_addr, 
       for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) * f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) tmem_st8p(o_addr + i * 8, a + 8 * i);
+      if (kSecond) {
+        // the first half of this key tile has already stored its P against the old reference (P.V of the tile is issued after
+        // both halves): bring those 16 columns to the new one as well
+        uint32_t pp[16];
+        tmem_ld16(p_addr - 16, pp);
+        tmem_wait_ld();
+        const f32x2 f2 = pack2(f, f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pp[i] = pack_bf16_pair(mul2(bf16x2_to_f32x2(pp[i]), f2));
+        tmem_st8p(p_addr - 16, pp);
+        tmem_st8p(p_addr - 8, pp + 8);
+      }
+      tmem_wait_st();   // the next half tile may rescale again: its loads must see these stores
     }
     lsum *= f;
     m_ref = mn;
   }
   const f32x2 negm2 = pack2(-m_ref, -m_ref);
   f32x2 s2a = pack2(0.f, 0.f), s2b = pack2(0.f, 0.f);
+  // MUFU turn (see "MUFU token" in the kernel): the exponentials of the two main streams' warps of one SM sub-partition
+  // alternate instead of sharing the MUFU half and half, so that each warp's score load / maximum / P store / barrier
+  // traffic runs under the other warp's exponentials
+  if (tok_wait) named_bar_sync(tok_wait, 64);
 #pragma unroll
-  for (int i = 0; i < NC / 16; ++i) {
+  for (int i = 0; i < 2; ++i) {
     uint32_t pk[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       const int c = i * 16 + 2 * jj;
       const f32x2 x2 = add2(pack2(v[c], v[c + 1]), negm2);
       f32x2 e2;
-      if (AFT_V3_POLY > 0 && jj % (AFT_V3_POLY > 0 ? AFT_V3_POLY : 1) == (AFT_V3_POLY > 0 ? AFT_V3_POLY : 1) - 1) {
+      if (((AFT_V3_POLY_MASK) >> jj) & 1) {
         e2 = ex2_poly2(x2);
       } else {
         float a, b;
@@ -206,17 +232,13 @@ __device__ __forceinline__ void softmax_tile3(uint32_t s_addr, uint32_t o_addr, 
       if (jj & 1) s2b = add2(s2b, e2); else s2a = add2(s2a, e2);
       pk[jj] = pack_bf16_pair(e2);
     }
-    tmem_st8(s_addr + i * 8, pk);
+    tmem_st8(p_addr + i * 8, pk);
   }
-  tmem_wait_st();
+  if (tok_pass) named_bar_arrive(tok_pass, 64);
   float sa, sb2, sc, sd;
   unpack2(s2a, sa, sb2);
   unpack2(s2b, sc, sd);
   lsum += (sa + sb2) + (sc + sd);
-  if (!waited) {
-    mbar_wait(pv_bar, pv_par);
-    tc_fence_after_sync();
-  }
 }
 
 // output accumulator (32 columns of head g) / l -> bf16 -> O image row r
@@ -243,15 +265,18 @@ __device__ __forceinline__ void epi_ln3(uint32_t acc_addr, uint32_t sb, uint32_t
   const uint32_t gam = vec + 4 * (which == 1 ? kVN1W : kVN2W);
   const uint32_t bet = vec + 4 * (which == 1 ? kVN1B : kVN2B);
   f32x2 s2 = pack2(0.f, 0.f), q2 = pack2(0.f, 0.f);
+  // blocks of 32 columns, the next block's accumulators in flight while the current one is processed
+  uint32_t buf[2][32];
+  tmem_ld_cols(acc_addr, buf[0]);
 #pragma unroll
   for (int blk = 0; blk < 4; ++blk) {
-    uint32_t acc[32];
-    tmem_ld_cols(acc_addr + blk * 32, acc);
+    uint32_t (&acc)[32] = buf[blk & 1];
     const uint32_t xrow = sb + OFF_X + (blk >> 1) * kXChunkBytes + r * 128;
     uint4 xr[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) xr[u] = ld_shared_v4(xrow + ((((blk & 1) * 4 + u) ^ (r & 7)) << 4));
     tmem_wait_ld();
+    if (blk < 3) tmem_ld_cols(acc_addr + (blk + 1) * 32, buf[(blk + 1) & 1]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float4 b0 = lds_f4(bias + (blk * 32 + u * 8) * 4), b1 = lds_f4(bias + (blk * 32 + u * 8) * 4 + 16);
@@ -273,6 +298,7 @@ __device__ __forceinline__ void epi_ln3(uint32_t acc_addr, uint32_t sb, uint32_t
     for (int i = 0; i < 4; ++i) tmem_st8p(acc_addr + blk * 32 + i * 8, acc + 8 * i);
   }
   tmem_wait_st();
+  tmem_ld_cols(acc_addr, buf[0]);
   float sa, sb2, qa, qb;
   unpack2(s2, sa, sb2);
   unpack2(q2, qa, qb);
@@ -282,10 +308,10 @@ __device__ __forceinline__ void epi_ln3(uint32_t acc_addr, uint32_t sb, uint32_t
   const f32x2 rstd2 = pack2(rstd, rstd), shift2 = pack2(-mean * rstd, -mean * rstd);
 #pragma unroll
   for (int blk = 0; blk < 4; ++blk) {
-    uint32_t y[32];
-    tmem_ld_cols(acc_addr + blk * 32, y);
+    uint32_t (&y)[32] = buf[blk & 1];
     const uint32_t xrow = sb + OFF_X + (blk >> 1) * kXChunkBytes + r * 128;
     tmem_wait_ld();
+    if (blk < 3) tmem_ld_cols(acc_addr + (blk + 1) * 32, buf[(blk + 1) & 1]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float4 g0 = lds_f4(gam + (blk * 32 + u * 8) * 4), g1 = lds_f4(gam + (blk * 32 + u * 8) * 4 + 16);
@@ -444,26 +470,30 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
       const uint32_t tm = tmem + 160 * s;
       uint32_t n_seq = 0, Lg = 0, hg = 0, n_in = 0, ring_base = 0;
       auto ring_wait = [&](uint32_t idx) -> uint32_t {
-        mbar_wait(bars + B_W_FULL + 8 * (idx % 3), (idx / 3) & 1);
+        mbar_wait_spin(bars + B_W_FULL + 8 * (idx % 3), (idx / 3) & 1);
         tc_fence_after_sync();
         return sb + OFF_QKV + (idx % 3) * kSlot;
       };
       auto ring_release = [&](uint32_t idx) { mma_commit(bars + B_W_EMPTY + 8 * (idx % 3), el); };
       for (int seq = blockIdx.x; seq < nseq; seq += gridDim.x, ++n_seq) {
-        mbar_wait(bars + B_X_FULL, n_seq & 1);
+        mbar_wait_spin(bars + B_X_FULL, n_seq & 1);
         for (int l = 0; l < L; ++l, ++Lg, ring_base += 8) {
+#ifdef AFT_V3_TIMELINE
+          const bool tl_on = blockIdx.x == 0 && n_seq == 1 && l == 1 && lane == 0 && s == 0;
+          uint32_t tl_n = 0;
+#endif
           // layer start: the stream's LayerNorm2 of the previous layer is written (X rows, accumulator columns and the
           // vector block are free as far as this stream is concerned)
-          if (Lg > 0) mbar_wait(sbar + S_X2_READY, (Lg - 1) & 1);
+          if (Lg > 0) mbar_wait_spin(sbar + S_X2_READY, (Lg - 1) & 1);
           tc_fence_after_sync();
           if (lane == 0) mbar_arrive(bars + B_QKV_FREE);
           __syncwarp();
           auto issue_qkv = [&](int g) {
             const int arow = s < 2 ? 128 * s : 256 - 32 * (g & 3);
-            mbar_wait(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
+            mbar_wait_spin(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
             tc_fence_after_sync();
             const uint32_t a0 = sb + OFF_X + arow * 128;
-            gemm_k128(tm, a0, a0 + kXChunkBytes, sb + OFF_W, sb + OFF_W + 96 * 128, kIdQkv, el);
+            gemm_k128(tm + 32, a0, a0 + kXChunkBytes, sb + OFF_W, sb + OFF_W + 96 * 128, kIdQkv, el);
             mma_commit(bars + B_W_EMPTY + 8 * kSlotIn, el);
             mma_commit(sbar + S_QKV_DONE, el);
             ++n_in;
@@ -471,8 +501,9 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
           issue_qkv(0);
           for (int g = 0; g < 4; ++g, ++hg) {
             const int arow = s < 2 ? 128 * s : 256 - 32 * (g & 3);
-            mbar_wait(bars + B_QKV_READY, hg & 1);
+            mbar_wait_spin(bars + B_QKV_READY, hg & 1);
             tc_fence_after_sync();
+            TL3(2, g * 100 + 1);
             const uint32_t qd = lo_k64(sb + OFF_QKV + arow * 64);
             const uint32_t kd = lo_k64(sb + OFF_QKV + kQkvPart);
             const uint32_t vd = lo_mn64(sb + OFF_QKV + 2 * kQkvPart);
@@ -482,49 +513,64 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
               for (int ks = 0; ks < 2; ++ks) mma_ss(d, d64(qd + ks * 2), d64(kd + j * 256 + ks * 2), j < 4 ? kIdS64 : kIdS32, ks > 0, el);
               mma_commit(sbar + S_S_DONE + 8 * (j & 1), el);
             };
+#ifdef AFT_V3_STAGGER_NS
+            if (s == 1) __nanosleep(AFT_V3_STAGGER_NS);   // experiment: phase-shift stream 1 against stream 0
+#endif
             issue_s(0);
             issue_s(1);
 #pragma unroll 1
             for (int j = 0; j < 5; ++j) {
               const uint32_t pidx = (j & 1) ? 2 * hg + (j >> 1) : 3 * hg + (j >> 1);
-              mbar_wait(sbar + S_P_READY + 8 * (j & 1), pidx & 1);
+              mbar_wait_spin(sbar + S_P_READY + 8 * (j & 1), pidx & 1);
               tc_fence_after_sync();
+              TL3(2, g * 100 + 10 + j);
               const int nks = j < 4 ? 4 : 2;
               for (int ks = 0; ks < nks; ++ks)
                 mma_ts(tm + 128, tm + 64 * (j & 1) + ks * 8, d64(vd + j * 256 + ks * 64), kIdPV, j > 0 || ks > 0, el);
               mma_commit(sbar + S_PV_DONE, el);
-              if (j + 2 <= 4 || (j == 4 && g < 3)) {
-                // the score buffer holds P(j) until P.V(j) has read it
-                mbar_wait(sbar + S_PV_DONE, (5 * hg + j) & 1);
-                tc_fence_after_sync();
-              }
+              // S(j + 2) overwrites the buffer that holds P(j): issued right behind P.V(j) -- tcgen05.mma instructions of one
+              // thread execute in issue order, so P.V(j) has read its A operand before the new scores land
               if (j + 2 <= 4) issue_s(j + 2);
+              TL3(2, g * 100 + 20 + j);
+              if (j == 3 && g < 3) {
+                // columns [32, 128) (upper half of buffer 0: the last key tile has 32 keys; buffer 1: P(3)) are free once
+                // P.V(3) has completed: the next head's projection runs under the last key tile
+                mbar_wait_spin(sbar + S_PV_DONE, (5 * hg + 3) & 1);
+                tc_fence_after_sync();
+                TL3(2, g * 100 + 30);
+                issue_qkv(g + 1);
+                TL3(2, g * 100 + 31);
+              }
             }
             // every P.V of this head by this stream has been issued: arrival when they complete
             mma_commit(bars + B_QKV_FREE, el);
             if (g == 3) mma_commit(bars + B_ATTN_DONE, el);
-            if (g < 3) issue_qkv(g + 1);
           }
           // ---- linear part of the layer on this stream's row tile
           const int arow = s < 2 ? 128 * s : 256 - 32 * (l & 3);
-          mbar_wait(sbar + S_O_READY, Lg & 1);
+          mbar_wait_spin(sbar + S_O_READY, Lg & 1);
           tc_fence_after_sync();
+          TL3(2, 1000);
           {
             const uint32_t w0 = ring_wait(ring_base + 0), w1 = ring_wait(ring_base + 1);
             const uint32_t a0 = sb + OFF_O + arow * 128;
+            TL3(2, 1001);
             gemm_k128(tm, a0, a0 + kXChunkBytes, w0, w1, kIdN128, el);
             mma_commit(sbar + S_OUT_DONE, el);
+            TL3(2, 1002);
             ring_release(ring_base + 0);
             ring_release(ring_base + 1);
           }
-          mbar_wait(sbar + S_X1_READY, Lg & 1);
+          mbar_wait_spin(sbar + S_X1_READY, Lg & 1);
           tc_fence_after_sync();
+          TL3(2, 1003);
           {
             const uint32_t xa0 = sb + OFF_X + arow * 128, xa1 = xa0 + kXChunkBytes;
             uint32_t w1a = 0, w1b = 0, w2 = 0;
             auto issue_f2 = [&](int c) {   // FFN2 partial product over hidden units 32 c .. 32 c + 31
-              mbar_wait(sbar + S_HID_READY + 8 * (c & 1), (c >> 1) & 1);
+              mbar_wait_spin(sbar + S_HID_READY + 8 * (c & 1), (c >> 1) & 1);
               tc_fence_after_sync();
+              TL3(2, 1030 + c);
               const int ch = c >> 1;   // 64-unit chunk = W2 K-chunk = hidden buffer ch & 1
               if ((c & 1) == 0) w2 = ring_wait(ring_base + (ch < 2 ? 3 + ch : 4 + ch));
               const uint32_t ha = sb + OFF_O + (ch & 1) * kXChunkBytes + arow * 128;
@@ -539,14 +585,16 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
             for (int c = 0; c < 8; ++c) {
               if ((c & 3) == 0) {
                 w1a = ring_wait(ring_base + (c == 0 ? 2 : 5));
-                mbar_wait(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
+                mbar_wait_spin(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
                 tc_fence_after_sync();
                 w1b = sb + OFF_W;
               }
-              if (c > 0) mbar_wait(sbar + S_F1_FREE, (c - 1) & 1);
+              if (c > 0) mbar_wait_spin(sbar + S_F1_FREE, (c - 1) & 1);
               tc_fence_after_sync();
+              TL3(2, 1010 + c);
               gemm_k128(tm + 128, xa0, xa1, w1a + 4096 * (c & 3), w1b + 4096 * (c & 3), kIdN32, el);
               mma_commit(sbar + S_F1_DONE, el);
+              TL3(2, 1020 + c);
               if ((c & 3) == 3) {
                 ring_release(ring_base + (c == 3 ? 2 : 5));
                 mma_commit(bars + B_W_EMPTY + 8 * kSlotIn, el);
@@ -569,60 +617,119 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + 160 * s;   // this thread's lane, this stream's columns
     const uint32_t vec = sb + OFF_VEC;
     uint32_t n_seq = 0, Lg = 0, hg = 0;
+    // MUFU token of SM sub-partition q: named barriers 1 + 2 q (stream 0's turn) and 2 + 2 q (stream 1's turn), 64 threads each
+    // (one warp syncs, the other arrives).  Every half tile of exponentials of stream 0 is followed by one of stream 1;
+    // stream 1 hands out the first turn.  The tail stream's warp is not part of the rotation.
+#ifndef AFT_V3_NO_TOKEN
+    const int tok_wait = s == 0 ? 1 + 2 * q : (s == 1 ? 2 + 2 * q : 0), tok_pass = s == 0 ? 2 + 2 * q : (s == 1 ? 1 + 2 * q : 0);
+    if (s == 1) named_bar_arrive(tok_pass, 64);
+#else
+    const int tok_wait = 0, tok_pass = 0;
+#endif
 #pragma unroll 1
     for (int seq = blockIdx.x; seq < nseq; seq += gridDim.x, ++n_seq) {
-      mbar_wait(bars + B_X_FULL, n_seq & 1);
+      mbar_wait_spin(bars + B_X_FULL, n_seq & 1);
 #pragma unroll 1
       for (int l = 0; l < L; ++l, ++Lg) {
+#ifdef AFT_V3_TIMELINE
+        const bool tl_on = blockIdx.x == 0 && n_seq == 1 && l == 1 && lane == 0 && (warp == 0 || warp == 4);
+        uint32_t tl_n = 0;
+        const int tl_slot = warp >> 2;
+#endif
 #pragma unroll 1
         for (int g = 0; g < 4; ++g, ++hg) {
           // Q/K/V region free: [layer start: every stream's LayerNorm2 of the previous layer], head g - 1 done by every stream
-          mbar_wait(bars + B_QKV_FREE, (5 * Lg + g) & 1);
+          if (s == 2 && q != (g & 3)) mbar_wait(bars + B_QKV_FREE, (5 * Lg + g) & 1); else mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + g) & 1);
           if (s == 2 && q != (g & 3)) continue;   // tail stream: the warp of quadrant g & 3 owns this head
-          mbar_wait(bars + B_BIAS_FULL + 8 * (g & 1), (hg >> 1) & 1);
-          mbar_wait(sbar + S_QKV_DONE, hg & 1);
+          TL3(tl_slot, g * 100 + 1);
+          mbar_wait_spin(bars + B_BIAS_FULL + 8 * (g & 1), (hg >> 1) & 1);
+          mbar_wait_spin(sbar + S_QKV_DONE, hg & 1);
           tc_fence_after_sync();
-          epi_qkv3(tl, sb, miscb + MISC_BIAS + (g & 1) * kBiasBytes3, r);
+          TL3(tl_slot, g * 100 + 2);
+          epi_qkv3(tl + 32, sb, miscb + MISC_BIAS + (g & 1) * kBiasBytes3, r);
           tc_fence_before_sync();
           fence_proxy_async_smem();
           warp_arrive(bars + B_QKV_READY, lane);
+          TL3(tl_slot, g * 100 + 3);
           float m_ref = -INFINITY, lsum = 0.f;
+          // Key loop, software-pipelined by half tiles of 32 keys: the scores of the next half tile travel TMEM -> registers
+          // while the exponentials of the current one run (tcgen05.wait::ld waits for every load in flight, so a load is
+          // issued right after the wait that completes its predecessor).  xa: first half of a key tile, xb: second half.
+          uint32_t xa[32], xb[32];
+          mbar_wait_spin(sbar + S_S_DONE, (3 * hg) & 1);
+          tc_fence_after_sync();
+          TL3(tl_slot, g * 100 + 4);
+          tmem_ld_cols(tl, xa);
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
-            const uint32_t sidx = (j & 1) ? 2 * hg + (j >> 1) : 3 * hg + (j >> 1);
-            mbar_wait(sbar + S_S_DONE + 8 * (j & 1), sidx & 1);
-            tc_fence_after_sync();
-            softmax_tile3<64>(tl + 64 * (j & 1), tl + 128, j == 0, sbar + S_PV_DONE, (5 * hg + j - 1) & 1, m_ref, lsum);
+            const uint32_t sbuf = tl + 64 * (j & 1);
+            bool pv_waited = false;
+            tmem_wait_ld();
+            TL3(tl_slot, g * 100 + 10 + j);
+            tmem_ld_cols(sbuf + 32, xb);
+            softmax_half3<false, false>(xa, sbuf, tl + 128, j == 0, j > 0, sbar + S_PV_DONE, (5 * hg + j - 1) & 1, pv_waited, m_ref, lsum, tok_wait, tok_pass);
+            TL3(tl_slot, g * 100 + 20 + j);
+            tmem_wait_ld();
+            {   // scores of the next key tile (tile 4: 32 keys) are complete long before: two score buffers
+              const int jn = j + 1;
+              const uint32_t sidx = (jn & 1) ? 2 * hg + (jn >> 1) : 3 * hg + (jn >> 1);
+              mbar_wait_spin(sbar + S_S_DONE + 8 * (jn & 1), sidx & 1);
+              tc_fence_after_sync();
+              tmem_ld_cols(tl + 64 * (jn & 1), xa);
+              TL3(tl_slot, g * 100 + 30 + j);
+            }
+            softmax_half3<false, true>(xb, sbuf + 16, tl + 128, false, j > 0, sbar + S_PV_DONE, (5 * hg + j - 1) & 1, pv_waited, m_ref, lsum, tok_wait, tok_pass);
+            TL3(tl_slot, g * 100 + 40 + j);
+            tmem_wait_st();
+            if (j > 0 && !pv_waited) {
+              mbar_wait_spin(sbar + S_PV_DONE, (5 * hg + j - 1) & 1);
+              tc_fence_after_sync();
+            }
             tc_fence_before_sync();
             warp_arrive(sbar + S_P_READY + 8 * (j & 1), lane);
+            TL3(tl_slot, g * 100 + 50 + j);
           }
-          mbar_wait(sbar + S_S_DONE, (3 * hg + 2) & 1);
+          {
+            bool pv_waited = false;
+            tmem_wait_ld();
+            softmax_half3<true, false>(xa, tl, tl + 128, false, true, sbar + S_PV_DONE, (5 * hg + 3) & 1, pv_waited, m_ref, lsum, tok_wait, tok_pass);
+            tmem_wait_st();
+            if (!pv_waited) {
+              mbar_wait_spin(sbar + S_PV_DONE, (5 * hg + 3) & 1);
+              tc_fence_after_sync();
+            }
+            tc_fence_before_sync();
+            warp_arrive(sbar + S_P_READY, lane);
+            TL3(tl_slot, g * 100 + 61);
+          }
+          mbar_wait_spin(sbar + S_PV_DONE, (5 * hg + 4) & 1);
           tc_fence_after_sync();
-          softmax_tile3<32>(tl, tl + 128, false, sbar + S_PV_DONE, (5 * hg + 3) & 1, m_ref, lsum);
-          tc_fence_before_sync();
-          warp_arrive(sbar + S_P_READY, lane);
-          mbar_wait(sbar + S_PV_DONE, (5 * hg + 4) & 1);
-          tc_fence_after_sync();
+          TL3(tl_slot, g * 100 + 62);
           epi_o3(tl + 128, sb, g, r, lsum, valid);
+          TL3(tl_slot, g * 100 + 63);
           if (s == 2 || g == 3) {
             tc_fence_before_sync();
             fence_proxy_async_smem();
             warp_arrive(sbar + S_O_READY, lane);
           }
         }
-        mbar_wait(bars + B_QKV_FREE, (5 * Lg + 4) & 1);   // head 3 done by every stream (keeps every warp in step with the barrier)
+        if (s == 2 && q != (l & 3)) mbar_wait(bars + B_QKV_FREE, (5 * Lg + 4) & 1); else mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + 4) & 1);   // head 3 done by every stream (keeps every warp in step with the barrier)
         if (s == 2 && q != (l & 3)) continue;             // tail stream: the warp of quadrant l & 3 owns the linear part of this layer
-        mbar_wait(bars + B_VEC_FULL, Lg & 1);
-        mbar_wait(sbar + S_OUT_DONE, Lg & 1);
+        TL3(tl_slot, 1070);
+        mbar_wait_spin(bars + B_VEC_FULL, Lg & 1);
+        mbar_wait_spin(sbar + S_OUT_DONE, Lg & 1);
         tc_fence_after_sync();
+        TL3(tl_slot, 1071);
         epi_ln3(tl, sb, vec, 1, r, valid);
+        TL3(tl_slot, 1072);
         tc_fence_before_sync();
         fence_proxy_async_smem();
         warp_arrive(sbar + S_X1_READY, lane);
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
-          mbar_wait(sbar + S_F1_DONE, c & 1);
+          mbar_wait_spin(sbar + S_F1_DONE, c & 1);
           tc_fence_after_sync();
+          TL3(tl_slot, 1080 + c);
           uint32_t a[32];
           tmem_ld_cols(tl + 128, a);
           tmem_wait_ld();
@@ -632,7 +739,7 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
           act_chunk3(a, vec, c, p.activation, pk);
           const int ch = c >> 1;
           // hidden buffer ch & 1 still feeds the FFN2 partial products of chunk ch - 2
-          if (c >= 4 && (c & 1) == 0) mbar_wait(sbar + S_F2_DONE + 8 * (ch & 1), 0);
+          if (c >= 4 && (c & 1) == 0) mbar_wait_spin(sbar + S_F2_DONE + 8 * (ch & 1), 0);
           if (valid) {
             const uint32_t row = sb + OFF_O + (ch & 1) * kXChunkBytes + r * 128;
 #pragma unroll
@@ -641,11 +748,14 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
           }
           fence_proxy_async_smem();
           warp_arrive(sbar + S_HID_READY + 8 * (c & 1), lane);
+          TL3(tl_slot, 1090 + c);
         }
-        mbar_wait(sbar + S_F2_DONE, 1);
-        mbar_wait(sbar + S_F2_DONE + 8, 1);
+        mbar_wait_spin(sbar + S_F2_DONE, 1);
+        mbar_wait_spin(sbar + S_F2_DONE + 8, 1);
         tc_fence_after_sync();
+        TL3(tl_slot, 1098);
         epi_ln3(tl, sb, vec, 2, r, valid);
+        TL3(tl_slot, 1099);
         tc_fence_before_sync();
         fence_proxy_async_smem();
         warp_arrive(sbar + S_X2_READY, lane);
@@ -673,9 +783,26 @@ bool tc_encoder3_launch(char* x_images, const TcLayer* layers_dev, int num_layer
   ep.num_layers = num_layers;
   ep.activation = activation;
   ep.nseq = nseq;
+  ep.timeline = nullptr;
   const unsigned grid = (unsigned)(nseq < sm_count ? nseq : sm_count);
+#ifdef AFT_V3_TIMELINE
+  static unsigned long long* tl_dev = nullptr;
+  if (!tl_dev) cudaMalloc(&tl_dev, 3 * 256 * 8);
+  cudaMemsetAsync(tl_dev, 0, 3 * 256 * 8, st);
+  ep.timeline = tl_dev;
+#endif
   encoder3_kernel<<<grid, kThreads3, kSmem3, st>>>(ep);
   count_launch();
+#ifdef AFT_V3_TIMELINE
+  if (getenv("AFT_V3_TIMELINE_DUMP")) {
+    static unsigned long long host[3 * 256];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, tl_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    for (int sl = 0; sl < 3; ++sl)
+      for (int i = 1; i < 256 && host[sl * 256 + i]; ++i)
+        fprintf(stderr, "TL3 %d %llu %llu\n", sl, host[sl * 256 + i] >> 48, host[sl * 256 + i] & 0xFFFFFFFFFFFFull);
+  }
+#endif
   return check_launch("encoder3_kernel");
 }
 

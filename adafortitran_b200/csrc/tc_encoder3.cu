@@ -8,10 +8,10 @@
 //
 //   stream 0 : token rows   0..127   compute warps 0..3  + MMA issuer warp 13
 //   stream 1 : token rows 128..255   compute warps 4..7  + MMA issuer warp 14
-//   stream 2 : token rows 256..279   compute warps 8..11 + MMA issuer warp 15   (the 24-row tail; ONE of its warps is active
-//              at a time: the A operand of its M = 128 MMAs starts 32 q rows early, which puts the tail rows on the lanes
-//              of TMEM quadrant q = SM sub-partition q; q rotates with the head (attention) and with the layer (linear
-//              part), so that the tail's work is spread over the four sub-partitions)
+//   stream 2 : token rows 256..279   compute warps 8..11 + MMA issuer warp 15   (the 24-row tail; ONE of its warps works at a
+//              time: the A operand of its M = 128 MMAs starts 32 q rows early, which puts the tail rows on the lanes of TMEM
+//              quadrant q = SM sub-partition q; q rotates with the head (attention) and with the layer (linear part), so
+//              that the tail's work is spread over the four sub-partitions.  All four warps walk the stream's barriers.)
 //   warp 12  : producer (bulk copies of weights / the sequence image, result image back to global memory)
 //
 // ONE THREAD OWNS ONE TOKEN ROW in every epilogue: softmax statistics, LayerNorm sums, 1/l are thread-private -- no
@@ -49,7 +49,9 @@ using namespace tcm;
 #endif
 
 constexpr int kThreads3 = 512;
-constexpr int kRegsCompute3 = 152, kRegsCtrl3 = 56;   // 384 x 152 + 128 x 56 = 65,536
+// 384 x 144 + 128 x 80 = 65,536.  The MMA issuers run long static programs: with 56 registers they spilled, and every
+// reload sits on a hand-off (measured: 229.8 vs 233.8 ms per 65536 estimates)
+constexpr int kRegsCompute3 = 144, kRegsCtrl3 = 80;
 constexpr int kProducerWarp3 = 12, kMmaWarp0 = 13;
 constexpr float kRescale3 = 8.0f;
 
@@ -62,7 +64,8 @@ constexpr uint32_t OFF_O = 0, OFF_X = 73728, OFF_QKV = 147456, OFF_W = 202752, O
 constexpr uint32_t kQkvPart = 18432, kSlot = 16384, kWInSlice = 24576;
 constexpr uint32_t OFF_VEC = OFF_QKV + 3 * kSlot;
 constexpr uint32_t kSmem3 = OFF_MISC + 5120;   // 232,448
-constexpr uint32_t MISC_BIAS = 0, MISC_BARS = 768, MISC_TMEM = 1280;
+constexpr uint32_t MISC_BIAS = 0, MISC_BARS = 768, MISC_TMEM = 1808;
+static_assert(MISC_BARS + 160 + 6 * 144 <= MISC_TMEM, "barrier block");
 
 // mbarriers (byte offsets from the barrier block).  "commit" = completed by tcgen05.commit / expect_tx, "warps" = one
 // arrival per compute warp.  Protocol rule (tc_ptx.cuh / DESIGN.md): a waiter tests phase parity, so completion k + 1 of a
@@ -78,13 +81,14 @@ enum : uint32_t {
   B_BIAS_FULL = 48,    // 2 x commit
   B_W_FULL = 64,       // 4 x commit : [0..2] ring slots, [3] in_proj slot
   B_W_EMPTY = 96,      // 4 x 3 commits
-  B_STREAM = 128,      // per-stream blocks of 128 bytes
+  B_QKV_FREE_T = 128,  // 4 x 3 arrivals: the same join, one barrier per tail quadrant (completes once per layer: before head q)
+  B_STREAM = 160,      // blocks of kStreamBars3 bytes: streams 0, 1, then the tail's four quadrant sets
 };
 enum : uint32_t {
-  S_QKV_DONE = 0, S_S_DONE = 8 /* 2 */, S_P_READY = 24 /* 2 */, S_PV_DONE = 40, S_O_READY = 48, S_OUT_DONE = 56, S_X1_READY = 64,
+  S_QKV_DONE = 0, S_S_DONE = 8 /* 2 */, S_P_READY = 24 /* 2 */, S_PV_DONE = 128 /* 2 */, S_PROJ_OK = 40, S_O_READY = 48, S_OUT_DONE = 56, S_X1_READY = 64,
   S_F1_DONE = 72, S_F1_FREE = 80, S_HID_READY = 88 /* 2 */, S_F2_DONE = 104 /* 2 */, S_X2_READY = 120,
 };
-constexpr uint32_t kSlotIn = 3;
+constexpr uint32_t kSlotIn = 3, kStreamBars3 = 144;
 
 constexpr uint32_t kIdQkv = make_idesc_bf16(128, 96, false, false);
 constexpr uint32_t kIdS64 = make_idesc_bf16(128, 64, false, false), kIdS32 = make_idesc_bf16(128, 32, false, false);
@@ -112,6 +116,12 @@ __device__ __forceinline__ void tmem_st8p(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
 }
+
+#ifdef AFT_V3_MMA_POLL
+#define MMA_WAIT3 mbar_wait_poll
+#else
+#define MMA_WAIT3 mbar_wait_spin
+#endif
 
 struct Enc3Params {
   unsigned long long* timeline;   // -DAFT_V3_TIMELINE builds: [3][256] (id << 48 | clock) records of block 0 (compute warp 0, compute warp 4, MMA issuer 0)
@@ -161,8 +171,14 @@ __device__ __forceinline__ void epi_qkv3(uint32_t taddr, uint32_t sb, uint32_t b
 // wait has happened).
 template <bool kMask, bool kSecond>
 __device__ __forceinline__ void softmax_half3(const uint32_t (&x)[32], uint32_t p_addr, uint32_t o_addr, bool first, bool has_prev_pv,
-                                              uint32_t pv_bar, uint32_t pv_par, bool& pv_waited, float& m_ref, float& lsum, int tok_wait,
-                                              int tok_pass) {
+                                              uint32_t pv_bar, uint32_t pv_par, bool& pv_waited, float& m_ref, float& lsum,
+                                              unsigned long long* dbg = nullptr) {
+#ifdef AFT_V3_TIMELINE
+#define DBG3(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+#else
+#define DBG3(i) do { } while (0)
+#endif
+  DBG3(0);
   float v[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(x[c]);
@@ -174,6 +190,7 @@ __device__ __forceinline__ void softmax_half3(const uint32_t (&x)[32], uint32_t 
 #pragma unroll
   for (int c = 4; c < 32; c += 4) { m0 = fmaxf(m0, v[c]); m1 = fmaxf(m1, v[c + 1]); m2 = fmaxf(m2, v[c + 2]); m3 = fmaxf(m3, v[c + 3]); }
   const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  DBG3(1);
   if (__any_sync(0xFFFFFFFFu, mt > m_ref + kRescale3)) {
     const float mn = fmaxf(m_ref, mt);
     const float f = ex2(m_ref - mn);   // first half tile: exp2(-inf) = 0
@@ -208,12 +225,9 @@ __device__ __forceinline__ void softmax_half3(const uint32_t (&x)[32], uint32_t 
     lsum *= f;
     m_ref = mn;
   }
+  DBG3(2);
   const f32x2 negm2 = pack2(-m_ref, -m_ref);
   f32x2 s2a = pack2(0.f, 0.f), s2b = pack2(0.f, 0.f);
-  // MUFU turn (see "MUFU token" in the kernel): the exponentials of the two main streams' warps of one SM sub-partition
-  // alternate instead of sharing the MUFU half and half, so that each warp's score load / maximum / P store / barrier
-  // traffic runs under the other warp's exponentials
-  if (tok_wait) named_bar_sync(tok_wait, 64);
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     uint32_t pk[8];
@@ -232,9 +246,10 @@ __device__ __forceinline__ void softmax_half3(const uint32_t (&x)[32], uint32_t 
       if (jj & 1) s2b = add2(s2b, e2); else s2a = add2(s2a, e2);
       pk[jj] = pack_bf16_pair(e2);
     }
+    DBG3(3 + 2 * i);
     tmem_st8(p_addr + i * 8, pk);
+    DBG3(4 + 2 * i);
   }
-  if (tok_pass) named_bar_arrive(tok_pass, 64);
   float sa, sb2, sc, sd;
   unpack2(s2a, sa, sb2);
   unpack2(s2b, sc, sd);
@@ -369,13 +384,15 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
     mbar_init(bars + B_BIAS_FULL, 1);
     mbar_init(bars + B_BIAS_FULL + 8, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(bars + B_W_FULL + 8 * i, 1); mbar_init(bars + B_W_EMPTY + 8 * i, 3); }
-    for (int s = 0; s < 3; ++s) {
-      const uint32_t b = bars + B_STREAM + 128 * s, nw = s < 2 ? 4 : 1;
+    for (int i = 0; i < 4; ++i) mbar_init(bars + B_QKV_FREE_T + 8 * i, 3);
+    for (int s = 0; s < 6; ++s) {   // 0, 1: main streams; 2 + q: the tail's barrier set of lane quadrant q
+      const uint32_t b = bars + B_STREAM + kStreamBars3 * s, nw = s < 2 ? 4 : 1;
       mbar_init(b + S_QKV_DONE, 1);
       mbar_init(b + S_S_DONE, 1); mbar_init(b + S_S_DONE + 8, 1);
       mbar_init(b + S_P_READY, nw); mbar_init(b + S_P_READY + 8, nw);
-      mbar_init(b + S_PV_DONE, 1);
-      mbar_init(b + S_O_READY, 4);
+      mbar_init(b + S_PV_DONE, 1); mbar_init(b + S_PV_DONE + 8, 1);
+      mbar_init(b + S_PROJ_OK, 1);
+      mbar_init(b + S_O_READY, s < 2 ? 4 : 1);   // main streams: once per layer by every warp; tail: once per head by its owner
       mbar_init(b + S_OUT_DONE, 1);
       mbar_init(b + S_X1_READY, nw);
       mbar_init(b + S_F1_DONE, 1);
@@ -464,19 +481,27 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
     } else {
       // ----------------------------------------------------------------------------- MMA issuer of stream s
       // The whole warp runs the schedule converged; only tcgen05.mma / commit are predicated on the elected lane.
+      // Barrier sets: a main stream has one; the tail has one per lane quadrant (set q serves the heads with g & 3 == q and the
+      // layers with l & 3 == q), so that every compute warp walks every phase of every barrier it waits on.  hv / lv number
+      // the visits of a set: main streams: heads / layers done; tail set q: one head per layer, one layer in four.
       const int s = warp - kMmaWarp0;
       const bool el = elect_one();
-      const uint32_t sbar = bars + B_STREAM + 128 * s;
       const uint32_t tm = tmem + 160 * s;
-      uint32_t n_seq = 0, Lg = 0, hg = 0, n_in = 0, ring_base = 0;
+      uint32_t n_seq = 0, Lg = 0, hg = 0, n_in = 0, ring_base = 0, n_proj = 0;
+      auto set_bar = [&](int qq) -> uint32_t { return bars + B_STREAM + kStreamBars3 * (s < 2 ? s : 2 + qq); };
+      auto lin_visits = [&](uint32_t nsq, int ll) -> uint32_t {   // visits of the linear-part set of layer ll before (nsq, ll)
+        if (s < 2) return nsq * (uint32_t)L + (uint32_t)ll;
+        const int qq = ll & 3;
+        return nsq * (uint32_t)(qq < L ? ((L - 1 - qq) >> 2) + 1 : 0) + (uint32_t)(ll >> 2);
+      };
       auto ring_wait = [&](uint32_t idx) -> uint32_t {
-        mbar_wait_spin(bars + B_W_FULL + 8 * (idx % 3), (idx / 3) & 1);
+        MMA_WAIT3(bars + B_W_FULL + 8 * (idx % 3), (idx / 3) & 1);
         tc_fence_after_sync();
         return sb + OFF_QKV + (idx % 3) * kSlot;
       };
       auto ring_release = [&](uint32_t idx) { mma_commit(bars + B_W_EMPTY + 8 * (idx % 3), el); };
       for (int seq = blockIdx.x; seq < nseq; seq += gridDim.x, ++n_seq) {
-        mbar_wait_spin(bars + B_X_FULL, n_seq & 1);
+        MMA_WAIT3(bars + B_X_FULL, n_seq & 1);
         for (int l = 0; l < L; ++l, ++Lg, ring_base += 8) {
 #ifdef AFT_V3_TIMELINE
           const bool tl_on = blockIdx.x == 0 && n_seq == 1 && l == 1 && lane == 0 && s == 0;
@@ -484,24 +509,30 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
 #endif
           // layer start: the stream's LayerNorm2 of the previous layer is written (X rows, accumulator columns and the
           // vector block are free as far as this stream is concerned)
-          if (Lg > 0) mbar_wait_spin(sbar + S_X2_READY, (Lg - 1) & 1);
+          if (Lg > 0) {
+            const int lp = l > 0 ? l - 1 : L - 1;
+            const uint32_t nsp = l > 0 ? n_seq : n_seq - 1;
+            MMA_WAIT3(set_bar(lp & 3) + S_X2_READY, lin_visits(nsp, lp) & 1);
+          }
           tc_fence_after_sync();
-          if (lane == 0) mbar_arrive(bars + B_QKV_FREE);
+          if (lane == 0) { mbar_arrive(bars + B_QKV_FREE); mbar_arrive(bars + B_QKV_FREE_T); }   // main streams' join; tail quadrant 0 (head 0)
           __syncwarp();
           auto issue_qkv = [&](int g) {
             const int arow = s < 2 ? 128 * s : 256 - 32 * (g & 3);
-            mbar_wait_spin(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
+            MMA_WAIT3(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
             tc_fence_after_sync();
             const uint32_t a0 = sb + OFF_X + arow * 128;
             gemm_k128(tm + 32, a0, a0 + kXChunkBytes, sb + OFF_W, sb + OFF_W + 96 * 128, kIdQkv, el);
             mma_commit(bars + B_W_EMPTY + 8 * kSlotIn, el);
-            mma_commit(sbar + S_QKV_DONE, el);
+            mma_commit(set_bar(g & 3) + S_QKV_DONE, el);
             ++n_in;
           };
           issue_qkv(0);
           for (int g = 0; g < 4; ++g, ++hg) {
             const int arow = s < 2 ? 128 * s : 256 - 32 * (g & 3);
-            mbar_wait_spin(bars + B_QKV_READY, hg & 1);
+            const uint32_t sbar = set_bar(g & 3);
+            const uint32_t hv = s < 2 ? hg : Lg;
+            MMA_WAIT3(bars + B_QKV_READY, hg & 1);
             tc_fence_after_sync();
             TL3(2, g * 100 + 1);
             const uint32_t qd = lo_k64(sb + OFF_QKV + arow * 64);
@@ -513,21 +544,22 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
               for (int ks = 0; ks < 2; ++ks) mma_ss(d, d64(qd + ks * 2), d64(kd + j * 256 + ks * 2), j < 4 ? kIdS64 : kIdS32, ks > 0, el);
               mma_commit(sbar + S_S_DONE + 8 * (j & 1), el);
             };
-#ifdef AFT_V3_STAGGER_NS
-            if (s == 1) __nanosleep(AFT_V3_STAGGER_NS);   // experiment: phase-shift stream 1 against stream 0
-#endif
             issue_s(0);
             issue_s(1);
 #pragma unroll 1
             for (int j = 0; j < 5; ++j) {
-              const uint32_t pidx = (j & 1) ? 2 * hg + (j >> 1) : 3 * hg + (j >> 1);
-              mbar_wait_spin(sbar + S_P_READY + 8 * (j & 1), pidx & 1);
+              const uint32_t pidx = (j & 1) ? 2 * hv + (j >> 1) : 3 * hv + (j >> 1);
+              MMA_WAIT3(sbar + S_P_READY + 8 * (j & 1), pidx & 1);
+              // tail: the first P.V of a head overwrites every lane of the output accumulator, also those of the quadrant whose
+              // warp may still be reading the previous head's result (another warp than the one that has just announced P)
+              if (s == 2 && j == 0 && g > 0) MMA_WAIT3(bars + B_STREAM + kStreamBars3 * 2 + S_O_READY, (4 * Lg + g - 1) & 1);
               tc_fence_after_sync();
               TL3(2, g * 100 + 10 + j);
               const int nks = j < 4 ? 4 : 2;
               for (int ks = 0; ks < nks; ++ks)
                 mma_ts(tm + 128, tm + 64 * (j & 1) + ks * 8, d64(vd + j * 256 + ks * 64), kIdPV, j > 0 || ks > 0, el);
-              mma_commit(sbar + S_PV_DONE, el);
+              mma_commit(sbar + S_PV_DONE + 8 * (j & 1), el);
+              if (j == 3 && g < 3) mma_commit(bars + B_STREAM + kStreamBars3 * s + S_PROJ_OK, el);   // this warp's own barrier: it waits for EVERY completion
               // S(j + 2) overwrites the buffer that holds P(j): issued right behind P.V(j) -- tcgen05.mma instructions of one
               // thread execute in issue order, so P.V(j) has read its A operand before the new scores land
               if (j + 2 <= 4) issue_s(j + 2);
@@ -535,7 +567,8 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
               if (j == 3 && g < 3) {
                 // columns [32, 128) (upper half of buffer 0: the last key tile has 32 keys; buffer 1: P(3)) are free once
                 // P.V(3) has completed: the next head's projection runs under the last key tile
-                mbar_wait_spin(sbar + S_PV_DONE, (5 * hg + 3) & 1);
+                MMA_WAIT3(bars + B_STREAM + kStreamBars3 * s + S_PROJ_OK, n_proj & 1);
+                ++n_proj;
                 tc_fence_after_sync();
                 TL3(2, g * 100 + 30);
                 issue_qkv(g + 1);
@@ -544,11 +577,14 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
             }
             // every P.V of this head by this stream has been issued: arrival when they complete
             mma_commit(bars + B_QKV_FREE, el);
+            if (g < 3) mma_commit(bars + B_QKV_FREE_T + 8 * (g + 1), el);   // the tail's owner of head g + 1 waits here
             if (g == 3) mma_commit(bars + B_ATTN_DONE, el);
           }
           // ---- linear part of the layer on this stream's row tile
           const int arow = s < 2 ? 128 * s : 256 - 32 * (l & 3);
-          mbar_wait_spin(sbar + S_O_READY, Lg & 1);
+          const uint32_t sbar = set_bar(l & 3);
+          const uint32_t lv = lin_visits(n_seq, l);
+          MMA_WAIT3(bars + B_STREAM + kStreamBars3 * s + S_O_READY, (s < 2 ? Lg : 4 * Lg + 3) & 1);   // (tail: one completion per head, in its set 0)
           tc_fence_after_sync();
           TL3(2, 1000);
           {
@@ -561,14 +597,14 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
             ring_release(ring_base + 0);
             ring_release(ring_base + 1);
           }
-          mbar_wait_spin(sbar + S_X1_READY, Lg & 1);
+          MMA_WAIT3(sbar + S_X1_READY, lv & 1);
           tc_fence_after_sync();
           TL3(2, 1003);
           {
             const uint32_t xa0 = sb + OFF_X + arow * 128, xa1 = xa0 + kXChunkBytes;
             uint32_t w1a = 0, w1b = 0, w2 = 0;
             auto issue_f2 = [&](int c) {   // FFN2 partial product over hidden units 32 c .. 32 c + 31
-              mbar_wait_spin(sbar + S_HID_READY + 8 * (c & 1), (c >> 1) & 1);
+              MMA_WAIT3(sbar + S_HID_READY + 8 * (c & 1), (c >> 1) & 1);
               tc_fence_after_sync();
               TL3(2, 1030 + c);
               const int ch = c >> 1;   // 64-unit chunk = W2 K-chunk = hidden buffer ch & 1
@@ -585,11 +621,11 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
             for (int c = 0; c < 8; ++c) {
               if ((c & 3) == 0) {
                 w1a = ring_wait(ring_base + (c == 0 ? 2 : 5));
-                mbar_wait_spin(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
+                MMA_WAIT3(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
                 tc_fence_after_sync();
                 w1b = sb + OFF_W;
               }
-              if (c > 0) mbar_wait_spin(sbar + S_F1_FREE, (c - 1) & 1);
+              if (c > 0) MMA_WAIT3(sbar + S_F1_FREE, (c - 1) & 1);
               tc_fence_after_sync();
               TL3(2, 1010 + c);
               gemm_k128(tm + 128, xa0, xa1, w1a + 4096 * (c & 3), w1b + 4096 * (c & 3), kIdN32, el);
@@ -609,23 +645,19 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
     }
   } else {
     // ----------------------------------------------------------------------------- compute warps
+    // Tail stream: warp 8 + q owns the heads with g & 3 == q and the linear part of the layers with l & 3 == q, on its own
+    // set of barriers; it takes no part in the rest.  (Two earlier schemes -- skipping the other owners' phases of shared
+    // barriers, or walking them without working -- were caught by the chaos build: a waiter must observe every phase of
+    // a barrier itself, and the arrivals it waits for must depend on its own progress.)
     setmaxnreg_inc<kRegsCompute3>();
     const int s = warp >> 2, q = warp & 3;
     const int r = s < 2 ? 128 * s + 32 * q + lane : 256 + lane;     // token row of this thread
     const bool valid = r < kS;
-    const uint32_t sbar = bars + B_STREAM + 128 * s;
+    const uint32_t sbar = bars + B_STREAM + kStreamBars3 * (s < 2 ? s : 2 + q);
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + 160 * s;   // this thread's lane, this stream's columns
     const uint32_t vec = sb + OFF_VEC;
+    const uint32_t lin_per_seq = s < 2 ? (uint32_t)L : (uint32_t)(q < L ? ((L - 1 - q) >> 2) + 1 : 0);
     uint32_t n_seq = 0, Lg = 0, hg = 0;
-    // MUFU token of SM sub-partition q: named barriers 1 + 2 q (stream 0's turn) and 2 + 2 q (stream 1's turn), 64 threads each
-    // (one warp syncs, the other arrives).  Every half tile of exponentials of stream 0 is followed by one of stream 1;
-    // stream 1 hands out the first turn.  The tail stream's warp is not part of the rotation.
-#ifndef AFT_V3_NO_TOKEN
-    const int tok_wait = s == 0 ? 1 + 2 * q : (s == 1 ? 2 + 2 * q : 0), tok_pass = s == 0 ? 2 + 2 * q : (s == 1 ? 1 + 2 * q : 0);
-    if (s == 1) named_bar_arrive(tok_pass, 64);
-#else
-    const int tok_wait = 0, tok_pass = 0;
-#endif
 #pragma unroll 1
     for (int seq = blockIdx.x; seq < nseq; seq += gridDim.x, ++n_seq) {
       mbar_wait_spin(bars + B_X_FULL, n_seq & 1);
@@ -639,11 +671,16 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
 #pragma unroll 1
         for (int g = 0; g < 4; ++g, ++hg) {
           // Q/K/V region free: [layer start: every stream's LayerNorm2 of the previous layer], head g - 1 done by every stream
-          if (s == 2 && q != (g & 3)) mbar_wait(bars + B_QKV_FREE, (5 * Lg + g) & 1); else mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + g) & 1);
-          if (s == 2 && q != (g & 3)) continue;   // tail stream: the warp of quadrant g & 3 owns this head
+          if (s < 2) {
+            mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + g) & 1);
+          } else {
+            if (q != (g & 3)) continue;
+            mbar_wait_spin(bars + B_QKV_FREE_T + 8 * q, Lg & 1);
+          }
+          const uint32_t hv = s < 2 ? hg : Lg;   // visits of this warp's barrier set so far
           TL3(tl_slot, g * 100 + 1);
           mbar_wait_spin(bars + B_BIAS_FULL + 8 * (g & 1), (hg >> 1) & 1);
-          mbar_wait_spin(sbar + S_QKV_DONE, hg & 1);
+          mbar_wait_spin(sbar + S_QKV_DONE, hv & 1);
           tc_fence_after_sync();
           TL3(tl_slot, g * 100 + 2);
           epi_qkv3(tl + 32, sb, miscb + MISC_BIAS + (g & 1) * kBiasBytes3, r);
@@ -656,68 +693,79 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
           // while the exponentials of the current one run (tcgen05.wait::ld waits for every load in flight, so a load is
           // issued right after the wait that completes its predecessor).  xa: first half of a key tile, xb: second half.
           uint32_t xa[32], xb[32];
-          mbar_wait_spin(sbar + S_S_DONE, (3 * hg) & 1);
+          mbar_wait_spin(sbar + S_S_DONE, (3 * hv) & 1);
           tc_fence_after_sync();
           TL3(tl_slot, g * 100 + 4);
           tmem_ld_cols(tl, xa);
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
             const uint32_t sbuf = tl + 64 * (j & 1);
+            // P.V(j - 1): only the (rare) rescale of the output accumulator has to wait for it.  P(j) goes to the buffer of S(j), whose
+            // last reader P.V(j - 2) completed before S(j) was written (in-order tensor pipe); that completion is consumed here
+            // anyway -- it costs one successful try_wait -- because every waiter must walk every phase of a barrier in order
+            // (the chaos build showed wrong-parity passes when this warp inferred a completion instead of observing it)
+            // (polling form: the arrival lands within nanoseconds of S_DONE(j); parking the warp for it cost 2 ms per 16384 estimates)
+            if (j >= 2) mbar_wait_poll(sbar + S_PV_DONE + 8 * (j & 1), ((((j - 2) & 1) ? 2 * hv : 3 * hv) + ((j - 2) >> 1)) & 1);
+            const int jm = j - 1;
+            const uint32_t pv_bar = sbar + S_PV_DONE + 8 * (jm & 1), pv_par = (((jm & 1) ? 2 * hv : 3 * hv) + (jm >> 1)) & 1;
             bool pv_waited = false;
             tmem_wait_ld();
             TL3(tl_slot, g * 100 + 10 + j);
             tmem_ld_cols(sbuf + 32, xb);
-            softmax_half3<false, false>(xa, sbuf, tl + 128, j == 0, j > 0, sbar + S_PV_DONE, (5 * hg + j - 1) & 1, pv_waited, m_ref, lsum, tok_wait, tok_pass);
+#ifdef AFT_V3_TIMELINE
+            unsigned long long dbgv[8];
+            softmax_half3<false, false>(xa, sbuf, tl + 128, j == 0, j > 0, pv_bar, pv_par, pv_waited, m_ref, lsum,
+                                        (tl_on && g == 1 && j == 1) ? dbgv : nullptr);
+            if (tl_on && g == 1 && j == 1)
+              for (int e = 0; e < 7; ++e) p.timeline[tl_slot * 256 + (++tl_n)] = ((unsigned long long)(900 + e) << 48) | (dbgv[e] & 0xFFFFFFFFFFFFull);
+#else
+            softmax_half3<false, false>(xa, sbuf, tl + 128, j == 0, j > 0, pv_bar, pv_par, pv_waited, m_ref, lsum);
+#endif
             TL3(tl_slot, g * 100 + 20 + j);
             tmem_wait_ld();
             {   // scores of the next key tile (tile 4: 32 keys) are complete long before: two score buffers
               const int jn = j + 1;
-              const uint32_t sidx = (jn & 1) ? 2 * hg + (jn >> 1) : 3 * hg + (jn >> 1);
+              const uint32_t sidx = (jn & 1) ? 2 * hv + (jn >> 1) : 3 * hv + (jn >> 1);
               mbar_wait_spin(sbar + S_S_DONE + 8 * (jn & 1), sidx & 1);
               tc_fence_after_sync();
               tmem_ld_cols(tl + 64 * (jn & 1), xa);
               TL3(tl_slot, g * 100 + 30 + j);
             }
-            softmax_half3<false, true>(xb, sbuf + 16, tl + 128, false, j > 0, sbar + S_PV_DONE, (5 * hg + j - 1) & 1, pv_waited, m_ref, lsum, tok_wait, tok_pass);
+            softmax_half3<false, true>(xb, sbuf + 16, tl + 128, false, j > 0, pv_bar, pv_par, pv_waited, m_ref, lsum);
             TL3(tl_slot, g * 100 + 40 + j);
             tmem_wait_st();
-            if (j > 0 && !pv_waited) {
-              mbar_wait_spin(sbar + S_PV_DONE, (5 * hg + j - 1) & 1);
-              tc_fence_after_sync();
-            }
             tc_fence_before_sync();
             warp_arrive(sbar + S_P_READY + 8 * (j & 1), lane);
             TL3(tl_slot, g * 100 + 50 + j);
           }
           {
             bool pv_waited = false;
+            mbar_wait_poll(sbar + S_PV_DONE, (3 * hv + 1) & 1);   // P.V(2), see above
             tmem_wait_ld();
-            softmax_half3<true, false>(xa, tl, tl + 128, false, true, sbar + S_PV_DONE, (5 * hg + 3) & 1, pv_waited, m_ref, lsum, tok_wait, tok_pass);
+            softmax_half3<true, false>(xa, tl, tl + 128, false, true, sbar + S_PV_DONE + 8, (2 * hv + 1) & 1, pv_waited, m_ref, lsum);
             tmem_wait_st();
-            if (!pv_waited) {
-              mbar_wait_spin(sbar + S_PV_DONE, (5 * hg + 3) & 1);
-              tc_fence_after_sync();
-            }
             tc_fence_before_sync();
             warp_arrive(sbar + S_P_READY, lane);
             TL3(tl_slot, g * 100 + 61);
           }
-          mbar_wait_spin(sbar + S_PV_DONE, (5 * hg + 4) & 1);
+          mbar_wait_spin(sbar + S_PV_DONE + 8, (2 * hv + 1) & 1);   // P.V(3)
+          mbar_wait_spin(sbar + S_PV_DONE, (3 * hv + 2) & 1);       // P.V(4)
           tc_fence_after_sync();
           TL3(tl_slot, g * 100 + 62);
           epi_o3(tl + 128, sb, g, r, lsum, valid);
           TL3(tl_slot, g * 100 + 63);
-          if (s == 2 || g == 3) {
+          if (s == 2 || g == 3) {   // main streams: once per layer and warp; tail: the owner of each head (set 0's barrier)
             tc_fence_before_sync();
             fence_proxy_async_smem();
-            warp_arrive(sbar + S_O_READY, lane);
+            warp_arrive(bars + B_STREAM + kStreamBars3 * s + S_O_READY, lane);
           }
         }
-        if (s == 2 && q != (l & 3)) mbar_wait(bars + B_QKV_FREE, (5 * Lg + 4) & 1); else mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + 4) & 1);   // head 3 done by every stream (keeps every warp in step with the barrier)
-        if (s == 2 && q != (l & 3)) continue;             // tail stream: the warp of quadrant l & 3 owns the linear part of this layer
+        if (s < 2) mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + 4) & 1);   // head 3 done by every stream: the main warps walk every phase of the join
+        else if (q != (l & 3)) continue;
+        const uint32_t lv = n_seq * lin_per_seq + (s < 2 ? (uint32_t)l : (uint32_t)(l >> 2));
         TL3(tl_slot, 1070);
-        mbar_wait_spin(bars + B_VEC_FULL, Lg & 1);
-        mbar_wait_spin(sbar + S_OUT_DONE, Lg & 1);
+        mbar_wait_spin(sbar + S_OUT_DONE, lv & 1);
+        mbar_wait_spin(bars + B_VEC_FULL, Lg & 1);   // (tail: skips the other owners' layers -- behind OUT_DONE, which this layer's vector block precedes causally)
         tc_fence_after_sync();
         TL3(tl_slot, 1071);
         epi_ln3(tl, sb, vec, 1, r, valid);

@@ -1668,14 +1668,14 @@ size_t tc_workspace_bytes(int64_t bc) {
          align_up_sz((size_t)bc * 3 * 2 * kS * sizeof(float), 1024);   // enhanced images | X images | adaptive features
 }
 
-// AFT_ENCODER=2|3|4 selects the encoder kernel (experiments / A-B runs); the default is compiled in
+// AFT_ENCODER=2|3 selects the encoder kernel (experiments / A-B runs); the default is compiled in
 #ifndef AFT_ENCODER_DEFAULT
 #define AFT_ENCODER_DEFAULT 2
 #endif
 static int encoder_version() {
   static const int v = [] {
     const char* e = getenv("AFT_ENCODER");
-    return e && (e[0] >= '2' && e[0] <= '4') ? e[0] - '0' : AFT_ENCODER_DEFAULT;
+    return e && (e[0] == '2' || e[0] == '3') ? e[0] - '0' : AFT_ENCODER_DEFAULT;
   }();
   return v;
 }
@@ -1704,9 +1704,7 @@ bool tc_forward_chunk(const TcWeights& w, const FrontPack& front, const HeadPack
   ep.timeline = g_timeline_arm;
   const unsigned grid = (unsigned)(nseq < sm_count ? nseq : sm_count);
   mark();
-  if (encoder_version() == 4) {
-    if (!tc_encoder4_launch(ximg, w.layers_dev, w.num_layers, activation, nseq, sm_count, st)) return false;
-  } else if (encoder_version() == 3) {
+  if (encoder_version() == 3) {
     if (!tc_encoder3_launch(ximg, w.layers_dev, w.num_layers, activation, nseq, sm_count, st)) return false;
   } else {
     encoder_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(ep);

@@ -8,10 +8,8 @@
 //
 //   stream 0 : token rows   0..127   compute warps 0..3  + MMA issuer warp 13
 //   stream 1 : token rows 128..255   compute warps 4..7  + MMA issuer warp 14
-//   stream 2 : token rows 256..279   compute warps 8..11 + MMA issuer warp 15   (the 24-row tail; ONE of its warps works at a
-//              time: the A operand of its M = 128 MMAs starts 32 q rows early, which puts the tail rows on the lanes of TMEM
-//              quadrant q = SM sub-partition q; q rotates with the head (attention) and with the layer (linear part), so
-//              that the tail's work is spread over the four sub-partitions.  All four warps walk the stream's barriers.)
+//   stream 2 : token rows 256..279   compute warp 8       + MMA issuer warp 15   (the 24-row tail: M = 128 MMAs whose rows
+//              280.. read whatever follows in shared memory -- rows of A are independent, those accumulator lanes are never read)
 //   warp 12  : producer (bulk copies of weights / the sequence image, result image back to global memory)
 //
 // ONE THREAD OWNS ONE TOKEN ROW in every epilogue: softmax statistics, LayerNorm sums, 1/l are thread-private -- no
@@ -64,8 +62,8 @@ constexpr uint32_t OFF_O = 0, OFF_X = 73728, OFF_QKV = 147456, OFF_W = 202752, O
 constexpr uint32_t kQkvPart = 18432, kSlot = 16384, kWInSlice = 24576;
 constexpr uint32_t OFF_VEC = OFF_QKV + 3 * kSlot;
 constexpr uint32_t kSmem3 = OFF_MISC + 5120;   // 232,448
-constexpr uint32_t MISC_BIAS = 0, MISC_BARS = 768, MISC_TMEM = 1808;
-static_assert(MISC_BARS + 160 + 6 * 144 <= MISC_TMEM, "barrier block");
+constexpr uint32_t MISC_BIAS = 0, MISC_BARS = 768, MISC_TMEM = 1344;
+static_assert(MISC_BARS + 128 + 3 * 144 <= MISC_TMEM, "barrier block");
 
 // mbarriers (byte offsets from the barrier block).  "commit" = completed by tcgen05.commit / expect_tx, "warps" = one
 // arrival per compute warp.  Protocol rule (tc_ptx.cuh / DESIGN.md): a waiter tests phase parity, so completion k + 1 of a
@@ -73,7 +71,7 @@ static_assert(MISC_BARS + 160 + 6 * 144 <= MISC_TMEM, "barrier block");
 // leave two completions behind are doubled (S_DONE, P_READY, HID_READY, F2_DONE) and used alternately.
 enum : uint32_t {
   B_X_FULL = 0,        // commit : sequence image landed
-  B_X_DONE = 8,        // warps(12): last LayerNorm of the sequence written
+  B_X_DONE = 8,        // warps(9) : last LayerNorm of the sequence written
   B_ATTN_DONE = 16,    // 3 commits: all P.V of the layer complete (producer: ring / vector block may overwrite Q/K/V)
   B_QKV_READY = 24,    // warps(9) : Q/K/V rows of head g written by every stream
   B_QKV_FREE = 32,     // 3 arrivals: Q/K/V region free -- 5 completions per layer: [layer start], head 0..3 done
@@ -81,8 +79,7 @@ enum : uint32_t {
   B_BIAS_FULL = 48,    // 2 x commit
   B_W_FULL = 64,       // 4 x commit : [0..2] ring slots, [3] in_proj slot
   B_W_EMPTY = 96,      // 4 x 3 commits
-  B_QKV_FREE_T = 128,  // 4 x 3 arrivals: the same join, one barrier per tail quadrant (completes once per layer: before head q)
-  B_STREAM = 160,      // blocks of kStreamBars3 bytes: streams 0, 1, then the tail's four quadrant sets
+  B_STREAM = 128,      // per-stream blocks of kStreamBars3 bytes
 };
 enum : uint32_t {
   S_QKV_DONE = 0, S_S_DONE = 8 /* 2 */, S_P_READY = 24 /* 2 */, S_PV_DONE = 128 /* 2 */, S_PROJ_OK = 40, S_O_READY = 48, S_OUT_DONE = 56, S_X1_READY = 64,
@@ -376,7 +373,7 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
 
   if (threadIdx.x == 0) {
     mbar_init(bars + B_X_FULL, 1);
-    mbar_init(bars + B_X_DONE, 12);
+    mbar_init(bars + B_X_DONE, 9);
     mbar_init(bars + B_ATTN_DONE, 3);
     mbar_init(bars + B_QKV_READY, 9);
     mbar_init(bars + B_QKV_FREE, 3);
@@ -384,15 +381,14 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
     mbar_init(bars + B_BIAS_FULL, 1);
     mbar_init(bars + B_BIAS_FULL + 8, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(bars + B_W_FULL + 8 * i, 1); mbar_init(bars + B_W_EMPTY + 8 * i, 3); }
-    for (int i = 0; i < 4; ++i) mbar_init(bars + B_QKV_FREE_T + 8 * i, 3);
-    for (int s = 0; s < 6; ++s) {   // 0, 1: main streams; 2 + q: the tail's barrier set of lane quadrant q
+    for (int s = 0; s < 3; ++s) {
       const uint32_t b = bars + B_STREAM + kStreamBars3 * s, nw = s < 2 ? 4 : 1;
       mbar_init(b + S_QKV_DONE, 1);
       mbar_init(b + S_S_DONE, 1); mbar_init(b + S_S_DONE + 8, 1);
       mbar_init(b + S_P_READY, nw); mbar_init(b + S_P_READY + 8, nw);
       mbar_init(b + S_PV_DONE, 1); mbar_init(b + S_PV_DONE + 8, 1);
       mbar_init(b + S_PROJ_OK, 1);
-      mbar_init(b + S_O_READY, s < 2 ? 4 : 1);   // main streams: once per layer by every warp; tail: once per head by its owner
+      mbar_init(b + S_O_READY, nw);
       mbar_init(b + S_OUT_DONE, 1);
       mbar_init(b + S_X1_READY, nw);
       mbar_init(b + S_F1_DONE, 1);
@@ -481,19 +477,12 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
     } else {
       // ----------------------------------------------------------------------------- MMA issuer of stream s
       // The whole warp runs the schedule converged; only tcgen05.mma / commit are predicated on the elected lane.
-      // Barrier sets: a main stream has one; the tail has one per lane quadrant (set q serves the heads with g & 3 == q and the
-      // layers with l & 3 == q), so that every compute warp walks every phase of every barrier it waits on.  hv / lv number
-      // the visits of a set: main streams: heads / layers done; tail set q: one head per layer, one layer in four.
       const int s = warp - kMmaWarp0;
       const bool el = elect_one();
       const uint32_t tm = tmem + 160 * s;
       uint32_t n_seq = 0, Lg = 0, hg = 0, n_in = 0, ring_base = 0, n_proj = 0;
-      auto set_bar = [&](int qq) -> uint32_t { return bars + B_STREAM + kStreamBars3 * (s < 2 ? s : 2 + qq); };
-      auto lin_visits = [&](uint32_t nsq, int ll) -> uint32_t {   // visits of the linear-part set of layer ll before (nsq, ll)
-        if (s < 2) return nsq * (uint32_t)L + (uint32_t)ll;
-        const int qq = ll & 3;
-        return nsq * (uint32_t)(qq < L ? ((L - 1 - qq) >> 2) + 1 : 0) + (uint32_t)(ll >> 2);
-      };
+      const uint32_t sbar = bars + B_STREAM + kStreamBars3 * s;
+      const int arow = s < 2 ? 128 * s : 256;   // first token row of the stream's M = 128 tile
       auto ring_wait = [&](uint32_t idx) -> uint32_t {
         MMA_WAIT3(bars + B_W_FULL + 8 * (idx % 3), (idx / 3) & 1);
         tc_fence_after_sync();
@@ -509,29 +498,22 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
 #endif
           // layer start: the stream's LayerNorm2 of the previous layer is written (X rows, accumulator columns and the
           // vector block are free as far as this stream is concerned)
-          if (Lg > 0) {
-            const int lp = l > 0 ? l - 1 : L - 1;
-            const uint32_t nsp = l > 0 ? n_seq : n_seq - 1;
-            MMA_WAIT3(set_bar(lp & 3) + S_X2_READY, lin_visits(nsp, lp) & 1);
-          }
+          if (Lg > 0) MMA_WAIT3(sbar + S_X2_READY, (Lg - 1) & 1);
           tc_fence_after_sync();
-          if (lane == 0) { mbar_arrive(bars + B_QKV_FREE); mbar_arrive(bars + B_QKV_FREE_T); }   // main streams' join; tail quadrant 0 (head 0)
+          if (lane == 0) mbar_arrive(bars + B_QKV_FREE);
           __syncwarp();
-          auto issue_qkv = [&](int g) {
-            const int arow = s < 2 ? 128 * s : 256 - 32 * (g & 3);
+          auto issue_qkv = [&]() {
             MMA_WAIT3(bars + B_W_FULL + 8 * kSlotIn, n_in & 1);
             tc_fence_after_sync();
             const uint32_t a0 = sb + OFF_X + arow * 128;
             gemm_k128(tm + 32, a0, a0 + kXChunkBytes, sb + OFF_W, sb + OFF_W + 96 * 128, kIdQkv, el);
             mma_commit(bars + B_W_EMPTY + 8 * kSlotIn, el);
-            mma_commit(set_bar(g & 3) + S_QKV_DONE, el);
+            mma_commit(sbar + S_QKV_DONE, el);
             ++n_in;
           };
-          issue_qkv(0);
+          issue_qkv();
           for (int g = 0; g < 4; ++g, ++hg) {
-            const int arow = s < 2 ? 128 * s : 256 - 32 * (g & 3);
-            const uint32_t sbar = set_bar(g & 3);
-            const uint32_t hv = s < 2 ? hg : Lg;
+            const uint32_t hv = hg;
             MMA_WAIT3(bars + B_QKV_READY, hg & 1);
             tc_fence_after_sync();
             TL3(2, g * 100 + 1);
@@ -550,16 +532,13 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
             for (int j = 0; j < 5; ++j) {
               const uint32_t pidx = (j & 1) ? 2 * hv + (j >> 1) : 3 * hv + (j >> 1);
               MMA_WAIT3(sbar + S_P_READY + 8 * (j & 1), pidx & 1);
-              // tail: the first P.V of a head overwrites every lane of the output accumulator, also those of the quadrant whose
-              // warp may still be reading the previous head's result (another warp than the one that has just announced P)
-              if (s == 2 && j == 0 && g > 0) MMA_WAIT3(bars + B_STREAM + kStreamBars3 * 2 + S_O_READY, (4 * Lg + g - 1) & 1);
               tc_fence_after_sync();
               TL3(2, g * 100 + 10 + j);
               const int nks = j < 4 ? 4 : 2;
               for (int ks = 0; ks < nks; ++ks)
                 mma_ts(tm + 128, tm + 64 * (j & 1) + ks * 8, d64(vd + j * 256 + ks * 64), kIdPV, j > 0 || ks > 0, el);
               mma_commit(sbar + S_PV_DONE + 8 * (j & 1), el);
-              if (j == 3 && g < 3) mma_commit(bars + B_STREAM + kStreamBars3 * s + S_PROJ_OK, el);   // this warp's own barrier: it waits for EVERY completion
+              if (j == 3 && g < 3) mma_commit(sbar + S_PROJ_OK, el);   // this warp's own barrier: it waits for EVERY completion
               // S(j + 2) overwrites the buffer that holds P(j): issued right behind P.V(j) -- tcgen05.mma instructions of one
               // thread execute in issue order, so P.V(j) has read its A operand before the new scores land
               if (j + 2 <= 4) issue_s(j + 2);
@@ -567,24 +546,21 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
               if (j == 3 && g < 3) {
                 // columns [32, 128) (upper half of buffer 0: the last key tile has 32 keys; buffer 1: P(3)) are free once
                 // P.V(3) has completed: the next head's projection runs under the last key tile
-                MMA_WAIT3(bars + B_STREAM + kStreamBars3 * s + S_PROJ_OK, n_proj & 1);
+                MMA_WAIT3(sbar + S_PROJ_OK, n_proj & 1);
                 ++n_proj;
                 tc_fence_after_sync();
                 TL3(2, g * 100 + 30);
-                issue_qkv(g + 1);
+                issue_qkv();
                 TL3(2, g * 100 + 31);
               }
             }
             // every P.V of this head by this stream has been issued: arrival when they complete
             mma_commit(bars + B_QKV_FREE, el);
-            if (g < 3) mma_commit(bars + B_QKV_FREE_T + 8 * (g + 1), el);   // the tail's owner of head g + 1 waits here
             if (g == 3) mma_commit(bars + B_ATTN_DONE, el);
           }
           // ---- linear part of the layer on this stream's row tile
-          const int arow = s < 2 ? 128 * s : 256 - 32 * (l & 3);
-          const uint32_t sbar = set_bar(l & 3);
-          const uint32_t lv = lin_visits(n_seq, l);
-          MMA_WAIT3(bars + B_STREAM + kStreamBars3 * s + S_O_READY, (s < 2 ? Lg : 4 * Lg + 3) & 1);   // (tail: one completion per head, in its set 0)
+          const uint32_t lv = Lg;
+          MMA_WAIT3(sbar + S_O_READY, Lg & 1);
           tc_fence_after_sync();
           TL3(2, 1000);
           {
@@ -645,18 +621,18 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
     }
   } else {
     // ----------------------------------------------------------------------------- compute warps
-    // Tail stream: warp 8 + q owns the heads with g & 3 == q and the linear part of the layers with l & 3 == q, on its own
-    // set of barriers; it takes no part in the rest.  (Two earlier schemes -- skipping the other owners' phases of shared
-    // barriers, or walking them without working -- were caught by the chaos build: a waiter must observe every phase of
-    // a barrier itself, and the arrivals it waits for must depend on its own progress.)
+    // Warps 9..11 only take part in setmaxnreg (whole warpgroups) and the final barrier: the tail is ONE warp on lane quadrant 0.
+    // (Rotating the tail over the quadrants to balance the sub-partitions was tried in three forms; the chaos build caught a
+    // barrier-phase problem in two of them and a data hazard in all -- the first P.V of the next head overwrites the accumulator
+    // lanes the previous owner is still reading -- and the fixed form measured slower than this one: DESIGN.md 4.1c.)
     setmaxnreg_inc<kRegsCompute3>();
+    if (warp < 9) {
     const int s = warp >> 2, q = warp & 3;
     const int r = s < 2 ? 128 * s + 32 * q + lane : 256 + lane;     // token row of this thread
     const bool valid = r < kS;
-    const uint32_t sbar = bars + B_STREAM + kStreamBars3 * (s < 2 ? s : 2 + q);
+    const uint32_t sbar = bars + B_STREAM + kStreamBars3 * s;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + 160 * s;   // this thread's lane, this stream's columns
     const uint32_t vec = sb + OFF_VEC;
-    const uint32_t lin_per_seq = s < 2 ? (uint32_t)L : (uint32_t)(q < L ? ((L - 1 - q) >> 2) + 1 : 0);
     uint32_t n_seq = 0, Lg = 0, hg = 0;
 #pragma unroll 1
     for (int seq = blockIdx.x; seq < nseq; seq += gridDim.x, ++n_seq) {
@@ -671,13 +647,8 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
 #pragma unroll 1
         for (int g = 0; g < 4; ++g, ++hg) {
           // Q/K/V region free: [layer start: every stream's LayerNorm2 of the previous layer], head g - 1 done by every stream
-          if (s < 2) {
-            mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + g) & 1);
-          } else {
-            if (q != (g & 3)) continue;
-            mbar_wait_spin(bars + B_QKV_FREE_T + 8 * q, Lg & 1);
-          }
-          const uint32_t hv = s < 2 ? hg : Lg;   // visits of this warp's barrier set so far
+          mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + g) & 1);
+          const uint32_t hv = hg;
           TL3(tl_slot, g * 100 + 1);
           mbar_wait_spin(bars + B_BIAS_FULL + 8 * (g & 1), (hg >> 1) & 1);
           mbar_wait_spin(sbar + S_QKV_DONE, hv & 1);
@@ -754,18 +725,17 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
           TL3(tl_slot, g * 100 + 62);
           epi_o3(tl + 128, sb, g, r, lsum, valid);
           TL3(tl_slot, g * 100 + 63);
-          if (s == 2 || g == 3) {   // main streams: once per layer and warp; tail: the owner of each head (set 0's barrier)
+          if (g == 3) {
             tc_fence_before_sync();
             fence_proxy_async_smem();
-            warp_arrive(bars + B_STREAM + kStreamBars3 * s + S_O_READY, lane);
+            warp_arrive(sbar + S_O_READY, lane);
           }
         }
-        if (s < 2) mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + 4) & 1);   // head 3 done by every stream: the main warps walk every phase of the join
-        else if (q != (l & 3)) continue;
-        const uint32_t lv = n_seq * lin_per_seq + (s < 2 ? (uint32_t)l : (uint32_t)(l >> 2));
+        mbar_wait_spin(bars + B_QKV_FREE, (5 * Lg + 4) & 1);   // head 3 done by every stream: every warp walks every phase of the join
+        const uint32_t lv = Lg;
         TL3(tl_slot, 1070);
         mbar_wait_spin(sbar + S_OUT_DONE, lv & 1);
-        mbar_wait_spin(bars + B_VEC_FULL, Lg & 1);   // (tail: skips the other owners' layers -- behind OUT_DONE, which this layer's vector block precedes causally)
+        mbar_wait_spin(bars + B_VEC_FULL, Lg & 1);
         tc_fence_after_sync();
         TL3(tl_slot, 1071);
         epi_ln3(tl, sb, vec, 1, r, valid);
@@ -809,6 +779,7 @@ __global__ void __launch_bounds__(kThreads3, 1) encoder3_kernel(Enc3Params p) {
         warp_arrive(sbar + S_X2_READY, lane);
       }
       warp_arrive(bars + B_X_DONE, lane);
+    }
     }
   }
 

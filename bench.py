@@ -38,7 +38,7 @@ SYS = dict(ofdm=dict(num_scs=120, num_symbols=14), pilot=dict(num_scs=12, num_sy
 FORTI = dict(model_type="fortitran", patch_size=(3, 2), num_layers=6, model_dim=128, num_head=4, activation="gelu",
              dropout=0.1, max_seq_len=512, pos_encoding_type="learnable")
 ADA = dict(FORTI, model_type="adafortitran", channel_adaptivity_hidden_sizes=[7, 42, 560], adaptive_token_length=6)
-ENCODER_SOURCES = ("tc_encoder.cu", "tc_ptx.cuh", "tc_layout.cuh", "tc_encoder.cuh")
+ENCODER_SOURCES = ("tc_encoder.cu", "tc_ptx.cuh", "tc_layout.cuh", "tc_encoder.cuh", "tc_math.cuh")
 
 
 def parse():
@@ -410,7 +410,7 @@ def run_ours(args):
     if enc_ms > 0 and args.precision == "bf16":
         ach = n_est * F_ENC_EST / (enc_ms / 1e3) / 1e12
         traffic, traffic_note = measured_traffic()
-        roof = {"bound": "tensor", "kernel": "encoder_kernel", "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
+        roof = {"bound": "tensor", "kernel": "encoder3_kernel" if os.environ.get("AFT_ENCODER", "")[:1] == "3" else "encoder_kernel", "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["sustained"], "frac_of_burst_peak": ach / pk["burst"], "traffic": traffic, "traffic_source": traffic_note,
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                 "launches": int(nl[1]), "avg_launch_ms": enc_ms / max(1, int(nl[1])),

@@ -110,7 +110,7 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar = sb + OFF_BAR;
   float* xin = reinterpret_cast<float*>(smem + OFF_BAR + 64);   // [24]
-  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(bar, kIssuers); mbar_init(bar + 8, kIssuers); fence_mbar_init(); }
   if (warp == 1) { tmem_alloc(bar + 16, 512); tmem_relinquish(); }
   stack_init(smem, pack);
   tc_fence_before_sync();
@@ -200,7 +200,7 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
   if ((sb & 1023u) != 0) __trap();
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar = sb + OFF_BAR;
-  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); mbar_init(bar + 32, 1); mbar_init(bar + 40, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(bar, kIssuers); mbar_init(bar + 8, kIssuers); mbar_init(bar + 32, 1); mbar_init(bar + 40, 3); fence_mbar_init(); }
   if (warp == 1) { tmem_alloc(bar + 16, 512); tmem_relinquish(); }
   stack_init(smem, pack);
   tc_fence_before_sync();
@@ -260,20 +260,22 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
             bulk_prefetch_l2(enh + nseq2 * (int64_t)kPix, kPix * sizeof(float));
           }
         }
+      }
+      if (warp < 3) {   // linear_2: one issuing warp per row tile (an issuing thread manages one MMA per ~65 clk)
+        const bool el = elect_one();
+        const int t = warp;
         mbar_wait(bar + 32, n_run & 1);
         tc_fence_after_sync();
         constexpr uint32_t kHi = (uint32_t)(desc_k_sw128_const() >> 32);
         const uint32_t lo = (uint32_t)desc_k_sw128_const();
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t a = lo | (((sb + kImgOff + c * kXChunkBytes + t * 128 * 128) >> 4) & 0x3FFF);
-              const uint32_t b = lo | (((sb + OFF_KEEP + c * 2048) >> 4) & 0x3FFF);
-              mma_ss(tmem + t * 16, ((uint64_t)kHi << 32) | (a + ks * 2), ((uint64_t)kHi << 32) | (b + ks * 2), kIdescL2, (c | ks) != 0, el);
-            }
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a = lo | (((sb + kImgOff + c * kXChunkBytes + t * 128 * 128) >> 4) & 0x3FFF);
+            const uint32_t b = lo | (((sb + OFF_KEEP + c * 2048) >> 4) & 0x3FFF);
+            mma_ss(tmem + t * 16, ((uint64_t)kHi << 32) | (a + ks * 2), ((uint64_t)kHi << 32) | (b + ks * 2), kIdescL2, (c | ks) != 0, el);
+          }
         mma_commit(bar + 40, el);
       }
       mbar_wait(bar + 32, n_run & 1);   // the enhanced image is read with generic loads below

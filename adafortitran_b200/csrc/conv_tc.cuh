@@ -31,6 +31,10 @@ constexpr int kPosGuard = 32;                 // positions of slack before p = 0
 constexpr int kPosAlloc = 2112;               // 32 guard + 2048 (16 M-tiles) + 32 guard
 constexpr int kPlaneBytes = kPosAlloc * 16;   // one 8-channel group: 33,792 bytes
 constexpr int kTiles = 16;
+#ifndef AFT_CONV_ISSUERS
+#define AFT_CONV_ISSUERS 4
+#endif
+constexpr int kIssuers = AFT_CONV_ISSUERS;       // warps that issue the MMAs of a conv layer (stack_run), = count of its two mbarriers
 
 // packed parameters of one conv stack (global memory, built by conv_tc_pack): byte offsets
 constexpr int kPkW2 = 0;                      // 5 tap pairs x [2 taps][32 cout][8 cin] bf16 = 5 x 1024 (tap 9 = zeros)
@@ -92,7 +96,7 @@ __device__ __forceinline__ void stack_init(uint8_t* smem, const uint8_t* __restr
 
 // Runs the stack on the fp32 padded plane at OFF_IN (interior filled by the caller, border zero) and leaves the fp32
 // result, unpadded [1680], at OFF_OUT.  All kThreads threads call it.  `bar` = shared address of two mbarriers
-// (count 1 each), `phase` = number of stacks this CTA has run before (parity of both barriers).
+// (count kIssuers each), `phase` = number of stacks this CTA has run before (parity of both barriers).
 __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t tmem, uint32_t bar, uint32_t phase) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool stamp_on = blockIdx.x == 0 && phase == 2; (void)stamp_on;
@@ -123,7 +127,10 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   AFT_CONV_STAMP(1);
 
   // ---- conv2 (8 -> 32) on the tensor core: 16 tiles x 5 tap pairs, K = 16 (8 channels x 2 taps)
-  if (warp == 0) {   // converged warp, elected lane issues (keeps the descriptor math in uniform registers)
+  // Four issuing warps (tile i by warp i % 4; the tiles have disjoint accumulators): one thread issues one tcgen05.mma per
+  // ~65 clk whatever its size, the tensor pipe takes these small ones every ~40 clk (tools/micro/mma_issue.cu) -- and the
+  // 368 MMAs of a stack are half of its run time.  Each issuer commits to the same mbarrier (count kIssuers).
+  if (warp < kIssuers) {   // converged warp, elected lane issues (keeps the descriptor math in uniform registers)
     const bool el = elect_one();
     tc_fence_after_sync();
     // K = 16 holds the 8 input channels of TWO taps: the second K half of the A descriptor (LBO) is the same plane seen
@@ -132,7 +139,7 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
     const uint32_t a_base = ((sb + OFF_A1 + kPosGuard * 16) >> 4) & 0x3FFF;   // + positions (16 B each == 1 address unit)
     const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW2, 512);
 #pragma unroll 1
-    for (int i = 0; i < kTiles; ++i)
+    for (int i = warp; i < kTiles; i += kIssuers)
 #pragma unroll
       for (int pr = 0; pr < 5; ++pr) {
         const int t0 = 2 * pr, t1 = pr < 4 ? 2 * pr + 1 : 2 * pr;
@@ -183,13 +190,13 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   AFT_CONV_STAMP(4);
 
   // ---- conv3 (32 -> 8) on the tensor core: 16 tiles x 9 taps x 2 K-steps, N = 16 (8 real + 8 zero output channels)
-  if (warp == 0) {
+  if (warp < kIssuers) {
     const bool el = elect_one();
     tc_fence_after_sync();
     const uint32_t a_lo = desc_lo_none(sb + OFF_MID + kPosGuard * 16, kPlaneBytes);
     const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW3, 256);
 #pragma unroll 1
-    for (int i = 0; i < kTiles; ++i)
+    for (int i = warp; i < kTiles; i += kIssuers)
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int shift = (t / 3 - 1) * kPW + (t % 3 - 1);

@@ -432,10 +432,10 @@ __global__ void conv_tc_pack_kernel(ConvPack src, uint8_t* __restrict__ dst) {
     const int t = 2 * pr + half;
     w2[i] = __float2bfloat16(t < 9 ? src.w1[(t * 8 + j) * 32 + co] : 0.f);   // src.w1 is [tap][cin 8][cout 32]
   }
-  if (i < 18 * 256) {          // conv3: [tap][kstep][half][cout 16][8]; couts 8..15 are zero
-    const int tk = i / 256, rem = i % 256, half = rem / 128, co = (rem % 128) / 8, j = rem % 8;
-    const int t = tk >> 1, ks = tk & 1, ci = ks * 16 + half * 8 + j;
-    w3[i] = __float2bfloat16(co < 8 ? src.w2[(t * 32 + ci) * 8 + co] : 0.f);     // src.w2 is [tap][cin 32][cout 8]
+  if (i < 6 * 512) {           // conv3: [dy][kstep][half][n 32 = dx * 8 + cout][8]; n >= 24 is zero
+    const int dk = i / 512, rem = i % 512, half = rem / 256, n = (rem % 256) / 8, j = rem % 8;
+    const int dy = dk >> 1, ks = dk & 1, ci = ks * 16 + half * 8 + j, dx = n >> 3, co = n & 7;
+    w3[i] = __float2bfloat16(n < 24 ? src.w2[((dy * 3 + dx) * 32 + ci) * 8 + co] : 0.f);   // src.w2 is [tap][cin 32][cout 8]
   }
   if (i < 72) { f[kF_w0 + i] = src.w0[i]; f[kF_w3 + i] = src.w3[i]; }
   if (i < 8) { f[kF_b0 + i] = src.b0[i]; f[kF_b2 + i] = src.b2[i]; }

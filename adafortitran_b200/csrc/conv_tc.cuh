@@ -13,8 +13,13 @@
 //
 //   conv2:  A = a1 plane, K 16 = 8 channels x 2 taps (the descriptor's LBO is the position offset between the two taps),
 //           B = [32 cout][2 taps x 8 cin] per tap pair                                         ->  5 MMAs / tile, N = 32
-//   conv3:  A = mid planes (32 channels = 2 K-steps),            B = [8+8 zero cout][16]       -> 18 MMAs / tile, N = 16
-// Accumulators: conv2 fills all 512 TMEM columns (16 tiles x 32), conv3 reuses the first 256.
+//   conv3:  the three taps of a filter ROW go on N (N 32 = 3 dx x 8 cout + 8 zero), the rows on K: per tile 3 dy x 2
+//           K-steps (32 channels) = 6 MMAs with A shifted by whole grid rows only; D[p][dx][co] is the contribution of
+//           position p to output p - dx, and since p +- 1 are the neighbouring TMEM lanes of the same warp (the border
+//           columns 0 and 15 of the 16-wide padded grid are never outputs) the epilogue adds the three with two warp
+//           shuffles per channel.  6 instead of 18 MMAs per tile: the tensor pipe takes >= 40 clk per instruction
+//           however narrow it is (tools/micro/mma_issue.cu), so the instruction count is the cost.
+// Accumulators: conv2 and conv3 each fill all 512 TMEM columns (16 tiles x 32).
 #pragma once
 
 #include "aft_internal.cuh"
@@ -38,7 +43,7 @@ constexpr int kIssuers = AFT_CONV_ISSUERS;       // warps that issue the MMAs of
 
 // packed parameters of one conv stack (global memory, built by conv_tc_pack): byte offsets
 constexpr int kPkW2 = 0;                      // 5 tap pairs x [2 taps][32 cout][8 cin] bf16 = 5 x 1024 (tap 9 = zeros)
-constexpr int kPkW3 = 9216;                   // 18 (tap, kstep) x [2 halves][16 cout][8] bf16 = 18 x 512
+constexpr int kPkW3 = 9216;                   // 6 (dy, kstep) x [2 halves][32 n = dx * 8 + cout, 24..31 zero][8] bf16 = 6 x 1024
 constexpr int kPkF32 = 18432;                 // fp32: w0[9][8] | b0[8] | b1[32] | b2[8] | w3[9][8] | b3[1] (+pad) = 200 floats
 constexpr int kPkBytes = 18432 + 800;         // 19,232
 constexpr int kF_w0 = 0, kF_b0 = 72, kF_b1 = 80, kF_b2 = 112, kF_w3 = 120, kF_b3 = 192;
@@ -76,7 +81,6 @@ __device__ unsigned long long g_conv_tl[32];
 #endif
 
 constexpr uint32_t kIdescConv2 = make_idesc_bf16(128, 32, false, false);
-constexpr uint32_t kIdescConv3 = make_idesc_bf16(128, 16, false, false);
 
 __device__ __forceinline__ bool interior(int p) {   // padded position -> is it a real pixel?
   const int r = p >> 4, c = p & 15;
@@ -189,22 +193,20 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   __syncthreads();
   AFT_CONV_STAMP(4);
 
-  // ---- conv3 (32 -> 8) on the tensor core: 16 tiles x 9 taps x 2 K-steps, N = 16 (8 real + 8 zero output channels)
+  // ---- conv3 (32 -> 8) on the tensor core: 16 tiles x 3 filter rows x 2 K-steps, N = 32 (3 dx x 8 cout + 8 zero columns)
   if (warp < kIssuers) {
     const bool el = elect_one();
     tc_fence_after_sync();
     const uint32_t a_lo = desc_lo_none(sb + OFF_MID + kPosGuard * 16, kPlaneBytes);
-    const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW3, 256);
+    const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW3, 512);
 #pragma unroll 1
     for (int i = warp; i < kTiles; i += kIssuers)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int shift = (t / 3 - 1) * kPW + (t % 3 - 1);
+      for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          mma_ss(tmem + i * 16, desc_join(a_lo + ks * (2 * kPlaneBytes / 16) + i * 128 + shift), desc_join(b_lo + (t * 2 + ks) * 32),
-                 kIdescConv3, (t | ks) != 0, el);
-      }
+          mma_ss(tmem + i * 32, desc_join(a_lo + ks * (2 * kPlaneBytes / 16) + i * 128 + (dy - 1) * kPW), desc_join(b_lo + (dy * 2 + ks) * 64),
+                 kIdescConv2, (dy | ks) != 0, el);
     mma_commit(bar + 8, el);
   }
   AFT_CONV_STAMP(5);
@@ -212,23 +214,28 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   tc_fence_after_sync();
   AFT_CONV_STAMP(6);
 
-  // ---- conv3 epilogue: + bias, ReLU, zero borders -> a3 (bf16, reuses the a1 group-0 plane: conv2 has consumed it)
+  // ---- conv3 epilogue: out[p] = D[p-1][dx=-1] + D[p][dx=0] + D[p+1][dx=+1] (neighbouring lanes), + bias, ReLU, zero
+  // borders -> a3 (bf16, reuses the a1 group-0 plane: conv2 has consumed it)
   {
     const int q = warp & 3, part = warp >> 2;
-#pragma unroll 1
+#pragma unroll 2
     for (int i = part; i < kTiles; i += 4) {
       const int p = i * 128 + q * 32 + lane;
-      uint32_t acc[8];
-      tmem_ld8p(tmem + ((uint32_t)(q * 32) << 16) + i * 16, acc);
+      uint32_t acc[24];
+      tmem_ld16p(tmem + ((uint32_t)(q * 32) << 16) + i * 32, acc);
+      tmem_ld8p(tmem + ((uint32_t)(q * 32) << 16) + i * 32 + 16, acc + 16);
       tmem_wait_ld();
       const bool in_img = interior(p);
+      float v[8];
+#pragma unroll
+      for (int co = 0; co < 8; ++co) {
+        const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(acc[co]), 1);
+        const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(acc[16 + co]), 1);
+        v[co] = fmaxf((l + r) + (__uint_as_float(acc[8 + co]) + fw[kF_b2 + co]), 0.f);
+      }
       uint32_t pk[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v0 = fmaxf(__uint_as_float(acc[2 * j]) + fw[kF_b2 + 2 * j], 0.f);
-        const float v1 = fmaxf(__uint_as_float(acc[2 * j + 1]) + fw[kF_b2 + 2 * j + 1], 0.f);
-        pk[j] = in_img ? pack_bf16x2(v0, v1) : 0u;
-      }
+      for (int j = 0; j < 4; ++j) pk[j] = in_img ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
       *reinterpret_cast<uint4*>(smem + OFF_A1 + (kPosGuard + p) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }

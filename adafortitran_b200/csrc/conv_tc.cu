@@ -17,41 +17,60 @@ namespace {
 #define AFT_HEAD_L2_TC 1    // 1: linear_2 of the head as tcgen05 MMAs over the staged encoder image, 0: SIMT dot products
 #endif
 
-// One item = (token row t, 8 consecutive model columns): 288 x 16 items = 9 per thread, processed three at a time so
-// that the six 16-byte reads of the positional table (L2 resident, 143 KB) of a batch are in flight together.
+// One item = (token row t, 4 consecutive model columns): 288 x 32 items = 18 per thread.  A thread keeps the same four
+// columns for all its items (512 threads = 16 rows x 32 column groups per pass), so its IN_DIM x 4 weights stay in
+// registers as packed fp32 pairs and an item costs IN_DIM / 4 shared loads of the token row (one row per warp: broadcast)
+// + IN_DIM * 2 FFMA2.  Items go three at a time so that the reads of the positional table (L2 resident, 143 KB) of a
+// batch are in flight together.  Same products in the same order as the scalar fmaf form.
 template <int IN_DIM>
-__device__ __forceinline__ void linear1_image(const float* __restrict__ posb, const float* tok, const float* w1t, char* base) {
-  constexpr int kItems = kSPad * (kD / 8), kPerThread = kItems / kThreads;   // 4608 / 512 = 9
-  static_assert(kItems % kThreads == 0 && kPerThread % 3 == 0, "item count must split evenly");
-  const int tid = threadIdx.x;
+__device__ __forceinline__ void linear1_image(const float* __restrict__ posb, const float* tok, const float* __restrict__ w1t, char* base) {
+  constexpr int kItems = kSPad * (kD / 4), kPerThread = kItems / kThreads;   // 9216 / 512 = 18
+  static_assert(kItems % kThreads == 0 && kPerThread % 3 == 0 && kThreads % (kD / 4) == 0, "item count must split evenly");
+  const int tid = threadIdx.x, c4 = (tid & 31) * 4, t0 = tid >> 5;
+  tcm::f32x2 w[IN_DIM][2];
+#pragma unroll
+  for (int k = 0; k < IN_DIM; ++k) {
+    const float4 wv = *reinterpret_cast<const float4*>(w1t + k * kD + c4);
+    w[k][0] = tcm::pack2(wv.x, wv.y); w[k][1] = tcm::pack2(wv.z, wv.w);
+  }
+  const int chunk_off = (c4 >> 6) * kXChunkBytes, unit = (c4 & 63) >> 3, sub = (c4 & 4) * 2;   // ximage_offset(t, c4), split
 #pragma unroll 1
   for (int b0 = 0; b0 < kPerThread; b0 += 3) {
-    float4 pa[3], pb[3];
+    float4 pa[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int it = tid + (b0 + j) * kThreads, t = it >> 4, c8 = (it & 15) * 8;
+      const int t = t0 + (b0 + j) * (kThreads / 32);
       const int tt = t < kS ? t : 0;   // rows 280..287 are zero padding (computed on a valid row, stored as zeros)
-      pa[j] = *reinterpret_cast<const float4*>(posb + tt * kD + c8);
-      pb[j] = *reinterpret_cast<const float4*>(posb + tt * kD + c8 + 4);
+      pa[j] = *reinterpret_cast<const float4*>(posb + tt * kD + c4);
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int it = tid + (b0 + j) * kThreads, t = it >> 4, c8 = (it & 15) * 8;
+      const int t = t0 + (b0 + j) * (kThreads / 32);
       const int tt = t < kS ? t : 0;
-      float acc[8] = {pa[j].x, pa[j].y, pa[j].z, pa[j].w, pb[j].x, pb[j].y, pb[j].z, pb[j].w};
+      tcm::f32x2 acc0 = tcm::pack2(pa[j].x, pa[j].y), acc1 = tcm::pack2(pa[j].z, pa[j].w);
+      float a[IN_DIM];
+      if (IN_DIM % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < IN_DIM; k += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(tok + tt * IN_DIM + k);
+          a[k] = v.x; a[k + 1] = v.y; a[k + 2] = v.z; a[k + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < IN_DIM; k += 2) {
+          const float2 v = *reinterpret_cast<const float2*>(tok + tt * IN_DIM + k);
+          a[k] = v.x; a[k + 1] = v.y;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < IN_DIM; ++k) {
-        const float a = tok[tt * IN_DIM + k];
-        const float4 wa = *reinterpret_cast<const float4*>(w1t + k * kD + c8);
-        const float4 wb = *reinterpret_cast<const float4*>(w1t + k * kD + c8 + 4);
-        acc[0] = fmaf(a, wa.x, acc[0]); acc[1] = fmaf(a, wa.y, acc[1]);
-        acc[2] = fmaf(a, wa.z, acc[2]); acc[3] = fmaf(a, wa.w, acc[3]);
-        acc[4] = fmaf(a, wb.x, acc[4]); acc[5] = fmaf(a, wb.y, acc[5]);
-        acc[6] = fmaf(a, wb.z, acc[6]); acc[7] = fmaf(a, wb.w, acc[7]);
+        const tcm::f32x2 aa = tcm::pack2(a[k], a[k]);
+        acc0 = tcm::fma2(aa, w[k][0], acc0);
+        acc1 = tcm::fma2(aa, w[k][1], acc1);
       }
-      uint4 pk = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
-      if (t >= kS) pk = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(base + ximage_offset(t, c8)) = pk;
+      uint2 pk = make_uint2(tcm::pack_bf16_pair(acc0), tcm::pack_bf16_pair(acc1));
+      if (t >= kS) pk = make_uint2(0, 0);
+      *reinterpret_cast<uint2*>(base + chunk_off + t * kChunkRowBytes + (((unit ^ (t & 7)) << 4) | sub)) = pk;
     }
   }
 }
@@ -110,7 +129,7 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar = sb + OFF_BAR;
   float* xin = reinterpret_cast<float*>(smem + OFF_BAR + 64);   // [24]
-  if (tid == 0) { mbar_init(bar, kIssuers); mbar_init(bar + 8, kIssuers); fence_mbar_init(); }
+  if (tid == 0) { stack_bar_init(bar); fence_mbar_init(); }
   if (warp == 1) { tmem_alloc(bar + 16, 512); tmem_relinquish(); }
   stack_init(smem, pack);
   tc_fence_before_sync();
@@ -123,8 +142,6 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
   const float* enh = reinterpret_cast<const float*>(smem + OFF_OUT);
   float* tok = reinterpret_cast<float*>(smem + OFF_SCRATCH);   // [280][in_dim]
   float* z = tok + 3360;                                       // [3][560]
-  float* w1t = z + 1680;                                       // [in_dim][128]
-  float* hid = w1t + 1536;                                     // [2][64]
   const int in_dim = p.in_dim;
   uint32_t n_run = 0;
 
@@ -164,7 +181,6 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
       const int a = f / kPatchW, b = f - a * kPatchW;
       tok[t * in_dim + f] = enh[(kPatchH * pi + a) * kGridW + kPatchW * pj + b];
     }
-    for (int i = tid; i < in_dim * kD; i += kThreads) w1t[i] = p.l1_wt[i];
     if (p.adaptive) {
       // adaptive features (fortitran.py:216): computed once per sample by adapter_kernel, 3 x 560 floats
       const float* zs = zin + sample * (int64_t)(3 * 2 * kS);
@@ -180,8 +196,8 @@ frontend_tc_kernel(FrontPack p, const uint8_t* __restrict__ pack, const float2* 
     if (st_on) g_conv_tl[13] = clock64();
 #endif
     // h = tok . W1^T + b1 + pos (encoders.py:67-68) -> bf16 operand image of the residual stream
-    if (in_dim == kPatchLen) linear1_image<kPatchLen>(p.posb, tok, w1t, reinterpret_cast<char*>(hb_out) + seq * (int64_t)kXImageBytes);
-    else linear1_image<kPatchLen + kAda>(p.posb, tok, w1t, reinterpret_cast<char*>(hb_out) + seq * (int64_t)kXImageBytes);
+    if (in_dim == kPatchLen) linear1_image<kPatchLen>(p.posb, tok, p.l1_wt, reinterpret_cast<char*>(hb_out) + seq * (int64_t)kXImageBytes);
+    else linear1_image<kPatchLen + kAda>(p.posb, tok, p.l1_wt, reinterpret_cast<char*>(hb_out) + seq * (int64_t)kXImageBytes);
     __syncthreads();   // scratch / result are overwritten by the next image
 #ifdef AFT_TC_TIMELINE
     if (st_on) g_conv_tl[14] = clock64();
@@ -200,7 +216,7 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
   if ((sb & 1023u) != 0) __trap();
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar = sb + OFF_BAR;
-  if (tid == 0) { mbar_init(bar, kIssuers); mbar_init(bar + 8, kIssuers); mbar_init(bar + 32, 1); mbar_init(bar + 40, 3); fence_mbar_init(); }
+  if (tid == 0) { stack_bar_init(bar); mbar_init(bar + 32, 1); mbar_init(bar + 40, 3); fence_mbar_init(); }
   if (warp == 1) { tmem_alloc(bar + 16, 512); tmem_relinquish(); }
   stack_init(smem, pack);
   tc_fence_before_sync();

@@ -24,6 +24,7 @@
 
 #include "aft_internal.cuh"
 #include "tc_layout.cuh"
+#include "tc_math.cuh"
 #include "tc_ptx.cuh"
 
 namespace aft {
@@ -39,7 +40,13 @@ constexpr int kTiles = 16;
 #ifndef AFT_CONV_ISSUERS
 #define AFT_CONV_ISSUERS 4
 #endif
-constexpr int kIssuers = AFT_CONV_ISSUERS;       // warps that issue the MMAs of a conv layer (stack_run), = count of its two mbarriers
+constexpr int kIssuers = AFT_CONV_ISSUERS;       // warps that issue the MMAs of a conv layer (stack_run), = count of its mbarriers
+static_assert(kIssuers == 4, "a commit round (tiles 4 r .. 4 r + 3) must be the tiles one epilogue pass of the 16 warps reads");
+// mbarriers of a stack run, byte offsets from the `bar` block (OFF_BAR): one per round of four tiles and layer
+constexpr uint32_t kBarConv2 = 192, kBarConv3 = 224;
+__device__ __forceinline__ void stack_bar_init(uint32_t bar) {
+  for (int r = 0; r < 4; ++r) { ptx::mbar_init(bar + kBarConv2 + 8 * r, kIssuers); ptx::mbar_init(bar + kBarConv3 + 8 * r, kIssuers); }
+}
 
 // packed parameters of one conv stack (global memory, built by conv_tc_pack): byte offsets
 constexpr int kPkW2 = 0;                      // 5 tap pairs x [2 taps][32 cout][8 cin] bf16 = 5 x 1024 (tap 9 = zeros)
@@ -99,8 +106,8 @@ __device__ __forceinline__ void stack_init(uint8_t* smem, const uint8_t* __restr
 }
 
 // Runs the stack on the fp32 padded plane at OFF_IN (interior filled by the caller, border zero) and leaves the fp32
-// result, unpadded [1680], at OFF_OUT.  All kThreads threads call it.  `bar` = shared address of two mbarriers
-// (count kIssuers each), `phase` = number of stacks this CTA has run before (parity of both barriers).
+// result, unpadded [1680], at OFF_OUT.  All kThreads threads call it.  `bar` = shared address of the barrier block
+// (stack_bar_init), `phase` = number of stacks this CTA has run before (parity of its barriers).
 __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t tmem, uint32_t bar, uint32_t phase) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool stamp_on = blockIdx.x == 0 && phase == 2; (void)stamp_on;
@@ -108,23 +115,37 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   const float* fw = reinterpret_cast<const float*>(smem + OFF_PK + kPkF32);
   const float* in = reinterpret_cast<const float*>(smem + OFF_IN);
 
-  // ---- conv1 (1 -> 8, ReLU) on CUDA cores: one interior position per thread iteration -> a1 group 0 (bf16)
-  for (int px = tid; px < kPix; px += kThreads) {
-    const int r = px / kGridW, c = px - r * kGridW;
-    float acc[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = fw[kF_b0 + o];
+  // ---- conv1 (1 -> 8, ReLU) on CUDA cores: one interior position per thread iteration -> a1 group 0 (bf16).  The 72
+  // weights stay in registers as packed fp32 pairs (FFMA2: same products, same order as the scalar form).
+  {
+    tcm::f32x2 w[9][4], b[4];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const float a = in[(r + t / 3) * kPW + c + t % 3];
       const float4 wa = *reinterpret_cast<const float4*>(fw + kF_w0 + t * 8), wb = *reinterpret_cast<const float4*>(fw + kF_w0 + t * 8 + 4);
-      acc[0] = fmaf(a, wa.x, acc[0]); acc[1] = fmaf(a, wa.y, acc[1]); acc[2] = fmaf(a, wa.z, acc[2]); acc[3] = fmaf(a, wa.w, acc[3]);
-      acc[4] = fmaf(a, wb.x, acc[4]); acc[5] = fmaf(a, wb.y, acc[5]); acc[6] = fmaf(a, wb.z, acc[6]); acc[7] = fmaf(a, wb.w, acc[7]);
+      w[t][0] = tcm::pack2(wa.x, wa.y); w[t][1] = tcm::pack2(wa.z, wa.w); w[t][2] = tcm::pack2(wb.x, wb.y); w[t][3] = tcm::pack2(wb.z, wb.w);
     }
-    const int p = (r + 1) * kPW + c + 1;
-    *reinterpret_cast<uint4*>(smem + OFF_A1 + (kPosGuard + p) * 16) =
-        make_uint4(pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f)), pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f)),
-                   pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f)), pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f)));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = tcm::pack2(fw[kF_b0 + 2 * j], fw[kF_b0 + 2 * j + 1]);
+    for (int px = tid; px < kPix; px += kThreads) {
+      const int r = px / kGridW, c = px - r * kGridW;
+      tcm::f32x2 acc[4] = {b[0], b[1], b[2], b[3]};
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float a = in[(r + t / 3) * kPW + c + t % 3];
+        const tcm::f32x2 aa = tcm::pack2(a, a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = tcm::fma2(aa, w[t][j], acc[j]);
+      }
+      const int p = (r + 1) * kPW + c + 1;
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo, hi;
+        tcm::unpack2(acc[j], lo, hi);
+        pk[j] = pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+      }
+      *reinterpret_cast<uint4*>(smem + OFF_A1 + (kPosGuard + p) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
   }
   fence_proxy_async_smem();
   __syncthreads();
@@ -143,7 +164,7 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
     const uint32_t a_base = ((sb + OFF_A1 + kPosGuard * 16) >> 4) & 0x3FFF;   // + positions (16 B each == 1 address unit)
     const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW2, 512);
 #pragma unroll 1
-    for (int i = warp; i < kTiles; i += kIssuers)
+    for (int i = warp, r = 0; i < kTiles; i += kIssuers, ++r) {
 #pragma unroll
       for (int pr = 0; pr < 5; ++pr) {
         const int t0 = 2 * pr, t1 = pr < 4 ? 2 * pr + 1 : 2 * pr;
@@ -151,11 +172,10 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
         const uint32_t lbo = pr < 4 ? (uint32_t)(shift1 - shift0) : 1u;        // in 16-byte units
         mma_ss(tmem + i * 32, desc_join((a_base + i * 128 + shift0) | (lbo << 16)), desc_join(b_lo + pr * 64), kIdescConv2, pr > 0, el);
       }
-    mma_commit(bar, el);
+      mma_commit(bar + kBarConv2 + 8 * r, el);   // round r = tiles 4 r .. 4 r + 3: its epilogue runs under the later rounds
+    }
   }
   AFT_CONV_STAMP(2);
-  mbar_wait(bar, phase & 1);
-  tc_fence_after_sync();
   AFT_CONV_STAMP(3);
 
   // ---- conv2 epilogue: + bias, ReLU, zero the border positions -> mid planes (4 groups of 8 channels, bf16)
@@ -168,7 +188,9 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
       b1[j] = b.x; b1[j + 1] = b.y; b1[j + 2] = b.z; b1[j + 3] = b.w;
     }
 #pragma unroll 2
-    for (int i = part; i < kTiles; i += 4) {
+    for (int i = part, r = 0; i < kTiles; i += 4, ++r) {
+      mbar_wait(bar + kBarConv2 + 8 * r, phase & 1);
+      tc_fence_after_sync();
       const int p = i * 128 + q * 32 + lane;
       uint32_t acc[32];
       tmem_ld16p(tmem + ((uint32_t)(q * 32) << 16) + i * 32, acc);
@@ -200,18 +222,17 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
     const uint32_t a_lo = desc_lo_none(sb + OFF_MID + kPosGuard * 16, kPlaneBytes);
     const uint32_t b_lo = desc_lo_none(sb + OFF_PK + kPkW3, 512);
 #pragma unroll 1
-    for (int i = warp; i < kTiles; i += kIssuers)
+    for (int i = warp, r = 0; i < kTiles; i += kIssuers, ++r) {
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
           mma_ss(tmem + i * 32, desc_join(a_lo + ks * (2 * kPlaneBytes / 16) + i * 128 + (dy - 1) * kPW), desc_join(b_lo + (dy * 2 + ks) * 64),
                  kIdescConv2, (dy | ks) != 0, el);
-    mma_commit(bar + 8, el);
+      mma_commit(bar + kBarConv3 + 8 * r, el);
+    }
   }
   AFT_CONV_STAMP(5);
-  mbar_wait(bar + 8, phase & 1);
-  tc_fence_after_sync();
   AFT_CONV_STAMP(6);
 
   // ---- conv3 epilogue: out[p] = D[p-1][dx=-1] + D[p][dx=0] + D[p+1][dx=+1] (neighbouring lanes), + bias, ReLU, zero
@@ -219,7 +240,9 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   {
     const int q = warp & 3, part = warp >> 2;
 #pragma unroll 2
-    for (int i = part; i < kTiles; i += 4) {
+    for (int i = part, r = 0; i < kTiles; i += 4, ++r) {
+      mbar_wait(bar + kBarConv3 + 8 * r, phase & 1);
+      tc_fence_after_sync();
       const int p = i * 128 + q * 32 + lane;
       uint32_t acc[24];
       tmem_ld16p(tmem + ((uint32_t)(q * 32) << 16) + i * 32, acc);
@@ -243,22 +266,33 @@ __device__ __forceinline__ void stack_run(uint8_t* smem, uint32_t sb, uint32_t t
   __syncthreads();
   AFT_CONV_STAMP(7);
 
-  // ---- conv4 (8 -> 1, no activation) on CUDA cores -> fp32 result, unpadded, at OFF_IN
-  for (int px = tid; px < kPix; px += kThreads) {
-    const int r = px / kGridW, c = px - r * kGridW;
-    float acc[4] = {fw[kF_b3], 0.f, 0.f, 0.f};   // four partial sums: short dependency chains
+  // ---- conv4 (8 -> 1, no activation) on CUDA cores -> fp32 result, unpadded, at OFF_OUT.  Weights in registers as
+  // packed pairs; four partial sums (two packed accumulators): short dependency chains, the order of the scalar form.
+  {
+    tcm::f32x2 w[9][4];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const int p = (r + t / 3) * kPW + c + t % 3;
-      const uint4 a = *reinterpret_cast<const uint4*>(smem + OFF_A1 + (kPosGuard + p) * 16);
-      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
       const float4 wa = *reinterpret_cast<const float4*>(fw + kF_w3 + t * 8), wb = *reinterpret_cast<const float4*>(fw + kF_w3 + t * 8 + 4);
-      acc[0] = fmaf(__uint_as_float(w[0] << 16), wa.x, acc[0]); acc[1] = fmaf(__uint_as_float(w[0] & 0xFFFF0000u), wa.y, acc[1]);
-      acc[2] = fmaf(__uint_as_float(w[1] << 16), wa.z, acc[2]); acc[3] = fmaf(__uint_as_float(w[1] & 0xFFFF0000u), wa.w, acc[3]);
-      acc[0] = fmaf(__uint_as_float(w[2] << 16), wb.x, acc[0]); acc[1] = fmaf(__uint_as_float(w[2] & 0xFFFF0000u), wb.y, acc[1]);
-      acc[2] = fmaf(__uint_as_float(w[3] << 16), wb.z, acc[2]); acc[3] = fmaf(__uint_as_float(w[3] & 0xFFFF0000u), wb.w, acc[3]);
+      w[t][0] = tcm::pack2(wa.x, wa.y); w[t][1] = tcm::pack2(wa.z, wa.w); w[t][2] = tcm::pack2(wb.x, wb.y); w[t][3] = tcm::pack2(wb.z, wb.w);
     }
-    reinterpret_cast<float*>(smem + OFF_OUT)[px] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const float b3 = fw[kF_b3];
+    for (int px = tid; px < kPix; px += kThreads) {
+      const int r = px / kGridW, c = px - r * kGridW;
+      tcm::f32x2 acc01 = tcm::pack2(b3, 0.f), acc23 = tcm::pack2(0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int p = (r + t / 3) * kPW + c + t % 3;
+        const uint4 a = *reinterpret_cast<const uint4*>(smem + OFF_A1 + (kPosGuard + p) * 16);
+        acc01 = tcm::fma2(tcm::bf16x2_to_f32x2(a.x), w[t][0], acc01);
+        acc23 = tcm::fma2(tcm::bf16x2_to_f32x2(a.y), w[t][1], acc23);
+        acc01 = tcm::fma2(tcm::bf16x2_to_f32x2(a.z), w[t][2], acc01);
+        acc23 = tcm::fma2(tcm::bf16x2_to_f32x2(a.w), w[t][3], acc23);
+      }
+      float a0, a1, a2, a3;
+      tcm::unpack2(acc01, a0, a1);
+      tcm::unpack2(acc23, a2, a3);
+      reinterpret_cast<float*>(smem + OFF_OUT)[px] = (a0 + a1) + (a2 + a3);
+    }
   }
   __syncthreads();
   AFT_CONV_STAMP(8);

@@ -643,9 +643,18 @@ int aft_forward_host_gather(AftHandle* h, const void* pilots, const float* snr, 
   const char* hp = static_cast<const char*>(pilots);
   char* ho = static_cast<char*>(out);
   int lane = 0;
-  for (int64_t c0 = 0; c0 < batch; c0 += hc, lane ^= 1) {
+  // Chunk sizes taper towards the end (.., hc, hc/2, hc/4, hc/4): the device-to-host copy of the last chunk is the only
+  // one that no compute hides, so the last chunk is small; partial waves of the small chunks are filled by the other lane.
+  int64_t bc = 0;
+  for (int64_t c0 = 0; c0 < batch; c0 += bc, lane ^= 1) {
     AftHandle::HostLane& ln = h->lanes[lane];
-    const int64_t bc = batch - c0 < hc ? batch - c0 : hc;
+    const int64_t rem = batch - c0;
+    bc = rem < hc ? rem : hc;
+    if (!h->generic && batch > hc && rem <= hc + hc / 2 && rem > hc / 4) {
+      bc = (rem / 2 + 63) / 64 * 64;
+      if (bc < hc / 4) bc = hc / 4;
+      if (bc > rem) bc = rem;
+    }
     char* din = static_cast<char*>(ln.d_in);
     float* dmeta = reinterpret_cast<float*>(din + (size_t)ln.cap * h->P * sizeof(float2));
     AFT_CUDA(cudaMemcpyAsync(din, hp + (size_t)c0 * h->P * sizeof(float2), (size_t)bc * h->P * sizeof(float2),

@@ -227,6 +227,9 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
 
   float* in = reinterpret_cast<float*>(smem + OFF_IN);
   const float* res = reinterpret_cast<const float*>(smem + OFF_OUT);
+  // persistent scratch (second a1 group): W2 image / weights 0..4095 | enhanced image 4096.. | real part 12288.. | complex64 staging row
+  constexpr uint32_t kStageOff = OFF_KEEP + 19456;
+  static_assert(12288 + kPix * 4 <= 19456 && 19456 + kPix * 8 <= kPlaneBytes, "staging row must fit behind the real part");
 #if AFT_HEAD_L2_TC
   // linear_2 on the tensor core.  The encoder's output image (2 K-chunks x 288 rows x 128 B, SWIZZLE_128B) is staged as ONE
   // contiguous 73,728-byte block starting 1024-aligned inside mid group 1 and running through groups 2 and 3 (dead between
@@ -414,17 +417,24 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
 #ifdef AFT_TC_TIMELINE
       if (st_on) g_conv_tl[22] = clock64();
 #endif
-      // torch.complex (fortitran.py:180): the real pass parks its result in shared memory; the imaginary pass stores
-      // both as interleaved complex64, 16 bytes (two estimates) per access, to every destination (the caller's buffer
-      // and, in the fused all-gather, the peers' gather buffers over NVLink)
+      // torch.complex (fortitran.py:180): the real pass parks its result in shared memory; the imaginary pass interleaves
+      // both as complex64 in a shared staging row (13,440 bytes), which one thread then hands to the copy engine: one
+      // bulk copy per destination (the caller's buffer and, in the fused all-gather, the peers' gather buffers over
+      // NVLink).  The stores to up to eight GPUs no longer occupy the SM's store path: they drain while the next sample
+      // is computed, and the staging row is only rewritten a whole sample later (bulk_wait_read at the start of a part 1).
       if (part == 0) {
         for (int i = tid; i < kPix; i += kThreads) re_keep[i] = res[i];
+        if (tid == 0) bulk_wait_read();   // the previous sample's copies have read the staging row (ordered before the
+                                          // staging writes below by the barriers of the next stack run)
       } else {
         for (int i = tid; i < kPix / 2; i += kThreads) {
           const float2 re2 = reinterpret_cast<const float2*>(re_keep)[i], im2 = reinterpret_cast<const float2*>(res)[i];
-          const float4 v = make_float4(re2.x, im2.x, re2.y, im2.y);
-          for (int d = 0; d < out.n; ++d) reinterpret_cast<float4*>(out.ptr[d] + sample * kPix)[i] = v;
+          reinterpret_cast<float4*>(smem + kStageOff)[i] = make_float4(re2.x, im2.x, re2.y, im2.y);
         }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0)
+          for (int d = 0; d < out.n; ++d) bulk_s2g(out.ptr[d] + sample * kPix, sb + kStageOff, kPix * sizeof(float2));
       }
       __syncthreads();
 #ifdef AFT_TC_TIMELINE
@@ -432,6 +442,7 @@ head_tc_kernel(HeadPack p, const uint8_t* __restrict__ pack, const uint8_t* __re
 #endif
     }
   }
+  if (tid == 0) bulk_wait_all();   // the last estimates have left
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);

@@ -2,7 +2,7 @@
 
 Gates (BASELINE.json north_star):
   * official : |delta NMSE| <= 0.05 dB against the reference forward on the 21-condition synthetic sweep;
-  * self-imposed: output-relative error against the fp64 oracle <= -45 dB for FortiTran and <= -37 dB for AdaFortiTran.
+  * self-imposed: output-relative error against the fp64 oracle <= -45 dB for FortiTran and <= -38 dB for AdaFortiTran.
     (AdaFortiTran feeds raw SNR/delay-spread/Doppler values (up to 1400) into the token features, so at random init the
     residual stream is dominated by metadata-driven components ~1e4 times larger than the pilot-driven ones; ANY bf16
     operand path loses those: the reference's own bf16 autocast reaches only -33.6 dB (probe P5), a numpy
@@ -56,7 +56,7 @@ def test_adafortitran_vs_oracle(sd):
     g = util.golden("golden_ada.npz")
     m = util.make_model("ada", weights=sd, precision="bf16")
     y = run(m, g["pilots"], g["snr"], g["ds"], g["dop"])
-    assert O.rel_err_db(y, g["out64"]) <= -37.0
+    assert O.rel_err_db(y, g["out64"]) <= -38.0       # measured -39.1 dB (profiles/r02_gates_report.json)
 
 
 def test_variants_relu_layers2_sinusoidal(sd):
@@ -64,15 +64,15 @@ def test_variants_relu_layers2_sinusoidal(sd):
     v = util.golden("golden_variants.npz")
     args = (g["pilots"][:4], g["snr"][:4], g["ds"][:4], g["dop"][:4])
     m = util.make_model("ada", weights=sd, precision="bf16", overrides={"activation": "relu"})
-    assert O.rel_err_db(run(m, *args), v["out_relu"]) <= -36.0
+    assert O.rel_err_db(run(m, *args), v["out_relu"]) <= -38.0
     m = util.make_model("ada", precision="bf16", overrides={"num_layers": 2},
                         weights={k: a for k, a in sd.items() if not any(f"layers.{i}." in k for i in range(2, 6))})
-    assert O.rel_err_db(run(m, *args), v["out_layers2"]) <= -36.0
+    assert O.rel_err_db(run(m, *args), v["out_layers2"]) <= -38.0
     m = util.make_model("ada", precision="bf16", overrides={"pos_encoding_type": "sinusoidal"})
     s2 = {k: a for k, a in sd.items() if "position_embeddings" not in k}
     s2["transformer_encoder.positional_encoding.pe"] = m.state_dict()["transformer_encoder.positional_encoding.pe"].cpu().numpy()
     m.load_state_dict(util.to_torch(s2))
-    assert O.rel_err_db(run(m, *args), v["out_sinusoidal"]) <= -36.0
+    assert O.rel_err_db(run(m, *args), v["out_sinusoidal"]) <= -38.0
 
 
 def test_sweep_delta_nmse(sd):

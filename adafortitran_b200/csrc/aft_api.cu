@@ -509,6 +509,13 @@ int make_dst(const AftHandle* h, float2* out, const AftGather* g, int64_t c0, Ou
     }
   }
   if (dst->n == 0) { set_error("aft_forward: no destination (NULL out and no gather plan)"); return AFT_ERR_INVALID; }
+  // the estimates leave as 16-byte vectors / bulk copies of whole rows (a row is pix * 8 bytes: a multiple of 16 for the
+  // reference grid, so an aligned base keeps every row aligned)
+  for (int d = 0; d < dst->n; ++d)
+    if ((reinterpret_cast<uintptr_t>(dst->ptr[d]) & 15) != 0) {
+      set_error("aft_forward: output buffer %d is not 16-byte aligned", d);
+      return AFT_ERR_INVALID;
+    }
   return AFT_OK;
 }
 

@@ -32,7 +32,7 @@ namespace convtc {
 
 using namespace ptx;
 
-constexpr int kThreads = 512;                 // 16 warps; thread 0 also issues the MMAs
+constexpr int kThreads = 512;                 // 16 warps; warps 0..3 also issue the MMAs (elected lane)
 constexpr int kPosGuard = 32;                 // positions of slack before p = 0 (taps reach back 17 positions)
 constexpr int kPosAlloc = 2112;               // 32 guard + 2048 (16 M-tiles) + 32 guard
 constexpr int kPlaneBytes = kPosAlloc * 16;   // one 8-channel group: 33,792 bytes
@@ -60,7 +60,7 @@ constexpr int OFF_A1 = 0;                               // 2 groups (second one 
 constexpr int OFF_MID = 2 * kPlaneBytes;                // 4 groups
 constexpr int OFF_PK = 6 * kPlaneBytes;                 // packed weights (kPkBytes)
 constexpr int OFF_IN = OFF_PK + 19456;                  // fp32 padded input plane [122][16] (7,808 B); reused for the fp32 output
-constexpr int OFF_BAR = OFF_IN + 7808;                  // 2 mbarriers + TMEM pointer + 24 input floats
+constexpr int OFF_BAR = OFF_IN + 7808;                  // callers' mbarriers (0..63: +16 = TMEM pointer) | 24 input floats | stack barriers (192..255)
 constexpr int kStackSmemBytes = OFF_BAR + 256;          // 230,272
 // After a stack has run, the mid planes are dead until the next conv2 epilogue rewrites positions [0, 2048) of every
 // group; the fp32 result and the callers' scratch live there (behind the 512-byte front guard, which must stay zero).

@@ -104,9 +104,9 @@ AFT_API const char* aft_last_error(void);
 /* Replaces the constructor BaseFortiTranEstimator.__init__ / _setup_dimensions / _build_architecture
  * (reference src/models/fortitran.py:23-126).  Validates the shape against what the kernels support and
  * allocates the packed-weight arena on the current device.  Supported: model_dim 128, 4 heads, ff 256, patch sizes
- * dividing the grid.  The reference default geometry (grid 120x14, pilots 12x2, patch 3x2) runs in both precisions;
- * any other geometry runs with AFT_FP32 only (shape-generic kernels) and aft_forward rejects AFT_BF16 for it
- * with AFT_ERR_UNSUPPORTED. */
+ * dividing the grid.  The reference default geometry (grid 120x14, pilots 12x2, patch 3x2) runs on kernels specialised
+ * for it in both precisions; any other geometry (e.g. 3276x14: 7644 tokens) runs on the shape-generic kernels: AFT_FP32
+ * on CUDA cores, AFT_BF16 on the long-sequence tensor-core path (sequence in global memory, streaming attention). */
 AFT_API int aft_create(const AftConfig* cfg, AftHandle** out);
 AFT_API void aft_destroy(AftHandle* h);
 
@@ -122,7 +122,7 @@ AFT_API size_t aft_workspace_bytes(const AftHandle* h, int64_t batch, int precis
 /* Replaces BaseFortiTranEstimator.forward (reference src/models/fortitran.py:145-182) on device buffers.
  *   pilots : complex64 [batch, pilot_scs, pilot_symbols], interleaved re/im        (device)
  *   snr, delay_spread, doppler : float32 [batch]; all NULL iff the handle is not adaptive (device)
- *   out    : complex64 [batch, num_scs, num_symbols], interleaved re/im            (device)
+ *   out    : complex64 [batch, num_scs, num_symbols], interleaved re/im            (device, 16-byte aligned)
  * Asynchronous on `stream`; no allocation, no host synchronisation. */
 AFT_API int aft_forward(AftHandle* h, const void* pilots, const float* snr, const float* delay_spread,
                 const float* doppler, void* out, int64_t batch, int precision,

@@ -182,10 +182,12 @@ def test_full_size_batch_properties(sd):
 
 def test_host_entry_point_bf16(sd):
     m = util.make_model("ada", weights=sd, precision="bf16")
-    p, snr, ds, dop = O.synthetic_batch(2048 + 9, seed=35)
-    y = run(m, p, snr, ds, dop)
-    yh = m.forward_host(torch.from_numpy(p), util.meta(snr, ds, dop)).numpy()
-    assert np.array_equal(y, yh)
+    # 2057: one tapered tail (1088 + 512 + 457); 5000: full chunks of 2048 followed by the tapering ones (aft_api.cu)
+    for b, seed in ((2048 + 9, 35), (5000, 36)):
+        p, snr, ds, dop = O.synthetic_batch(b, seed=seed)
+        y = run(m, p, snr, ds, dop)
+        yh = m.forward_host(torch.from_numpy(p), util.meta(snr, ds, dop)).numpy()
+        assert np.array_equal(y, yh), b
 
 
 def test_empty_batch_and_profile_api(sd):

@@ -6,6 +6,7 @@
 //   * LinearEstimator -- y = W x + b with W [out, in] (reference src/models/linear.py:60-95).  HBM bound on the result
 //     (4 * out bytes per sample against 4 * in read); W^T is staged in shared memory once per CTA.
 #include "aft_internal.cuh"
+#include "tc_ptx.cuh"
 
 namespace aft {
 
@@ -62,49 +63,89 @@ extract_pilots_kernel(const float2* __restrict__ grid, float2* __restrict__ pilo
   }
 }
 
-// LinearEstimator, weights in registers: thread <-> kOut output features (rows of W), samples streamed through shared
-// memory in groups of kGroup (x rows are broadcast reads: kIn / 4 LDS.128 feed kOut * kIn FMAs), coalesced stores.
-template <int kIn, int kOut>
-__global__ void __launch_bounds__(864)
+// LinearEstimator, weights in registers: thread <-> FOUR CONSECUTIVE output features (rows of W), each row held as
+// kIn / 2 packed fp32 pairs (w_k, w_k+1).  Samples are streamed through shared memory in groups of kGroup; a 16-byte
+// broadcast load delivers (x_k .. x_k+3), i.e. the packed operands of two FFMA2 per output: the accumulator pair of an
+// output holds its even-k and odd-k partial sums, added at the end.  The result leaves as ONE 16-byte store per thread and
+// sample: every variant with 4-byte stores (scalar FMA, FFMA2, 2 / 4 / 5 outputs per thread, 11 .. 27 warps) ran at the
+// same ~800 clk per sample and SM, i.e. one warp-wide store instruction per ~15 clk -- the store path is paid per
+// instruction, not per byte (a 16-byte-per-thread fill reaches 7.5 TB/s on this GPU, tools/write_bw.py).
+template <int kIn, int kOut, int kThreadsL>
+__global__ void __launch_bounds__(kThreadsL)
 linear_regw_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ y,
                    int64_t batch, int out_dim) {
+  static_assert(kIn % 4 == 0, "four k steps per shared load");
+  static_assert(kOut % 4 == 0, "16-byte stores");
   constexpr int kGroup = 64;
-  __shared__ __align__(16) float xs[2][kGroup * kIn];
-  const int nthr = (out_dim + kOut - 1) / kOut;          // threads that own outputs: o = tid + j * nthr
+  __shared__ __align__(16) float xs[2][kGroup * kIn + 4];   // + 4: the pipelined load runs one step past the last sample
+  const int nthr = out_dim / kOut;                          // out_dim % kOut == 0 (checked by the launcher)
   const bool owner = (int)threadIdx.x < nthr;
-  float wr[kOut][kIn], br[kOut];
+  unsigned long long wr[kOut][kIn / 2];
+  float br[kOut];
 #pragma unroll
   for (int j = 0; j < kOut; ++j) {
-    const int o = threadIdx.x + j * nthr;
-    const bool ok = owner && o < out_dim;
-    br[j] = ok ? bias[o] : 0.f;
+    const size_t o = (size_t)threadIdx.x * kOut + j;
+    br[j] = owner ? bias[o] : 0.f;
 #pragma unroll
-    for (int k = 0; k < kIn; ++k) wr[j][k] = ok ? w[(size_t)o * kIn + k] : 0.f;
+    for (int k2 = 0; k2 < kIn / 2; ++k2) {
+      const float a = owner ? w[o * kIn + 2 * k2] : 0.f, b = owner ? w[o * kIn + 2 * k2 + 1] : 0.f;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(wr[j][k2]) : "f"(a), "f"(b));
+    }
   }
+  // x groups arrive by 1-D bulk copies (one elected thread, completion on an mbarrier per buffer): the copy of group
+  // g + 1 is issued before group g is computed, so no warp ever waits for a global load
+  __shared__ __align__(8) unsigned long long bars[2];
+  const uint32_t bar0 = ptx::smem_u32(&bars[0]);
+  const int64_t stride = (int64_t)gridDim.x * kGroup;
+  auto fetch = [&](int64_t g0, int b) {
+    const uint32_t bytes = (uint32_t)((batch - g0 < kGroup ? batch - g0 : kGroup) * kIn * sizeof(float));
+    ptx::mbar_arrive_expect_tx(bar0 + 8 * b, bytes);
+    ptx::bulk_g2s(ptx::smem_u32(&xs[b][0]), x + g0 * kIn, bytes, bar0 + 8 * b);
+  };
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar0, 1);
+    ptx::mbar_init(bar0 + 8, 1);
+    ptx::fence_mbar_init();
+    if ((int64_t)blockIdx.x * kGroup < batch) fetch((int64_t)blockIdx.x * kGroup, 0);
+  }
+  __syncthreads();
   int buf = 0;
-  for (int64_t b0 = (int64_t)blockIdx.x * kGroup; b0 < batch; b0 += (int64_t)gridDim.x * kGroup, buf ^= 1) {
+  uint32_t it = 0;
+  for (int64_t b0 = (int64_t)blockIdx.x * kGroup; b0 < batch; b0 += stride, buf ^= 1, ++it) {
     const int nb = (int)(batch - b0 < kGroup ? batch - b0 : kGroup);
-    for (int i = threadIdx.x; i < nb * kIn; i += blockDim.x) xs[buf][i] = x[b0 * kIn + i];
-    __syncthreads();   // double buffered: the next group's stores cannot overtake this group's reads
+    __syncthreads();   // every warp has finished the previous group: its buffer may be refilled
+    if (threadIdx.x == 0 && b0 + stride < batch) {
+      ptx::fence_proxy_async_smem();
+      fetch(b0 + stride, buf ^ 1);
+    }
+    ptx::mbar_wait(bar0 + 8 * buf, (it >> 1) & 1);
     if (owner) {
-      for (int s = 0; s < nb; ++s) {
-        float acc[kOut];
+      float4* yp = reinterpret_cast<float4*>(y + b0 * out_dim) + threadIdx.x * (kOut / 4);
+      const ulonglong2* xp = reinterpret_cast<const ulonglong2*>(&xs[buf][0]);
+      ulonglong2 xa = xp[0];                               // software pipeline: the next 16 bytes of x are in flight
+      for (int s = 0; s < nb; ++s, yp += out_dim / 4, xp += kIn / 4) {
+        unsigned long long acc[kOut];
 #pragma unroll
-        for (int j = 0; j < kOut; ++j) acc[j] = br[j];
+        for (int j = 0; j < kOut; ++j) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[j]) : "f"(br[j]), "f"(0.f));
 #pragma unroll
         for (int k4 = 0; k4 < kIn / 4; ++k4) {
-          const float4 xv = *reinterpret_cast<const float4*>(&xs[buf][s * kIn + 4 * k4]);
+          const ulonglong2 xb = xp[k4 + 1];                // (x_k+4 .. x_k+7), or the next sample's first four (pad at the end)
 #pragma unroll
           for (int j = 0; j < kOut; ++j) {
-            acc[j] = fmaf(wr[j][4 * k4], xv.x, acc[j]); acc[j] = fmaf(wr[j][4 * k4 + 1], xv.y, acc[j]);
-            acc[j] = fmaf(wr[j][4 * k4 + 2], xv.z, acc[j]); acc[j] = fmaf(wr[j][4 * k4 + 3], xv.w, acc[j]);
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j]) : "l"(wr[j][2 * k4]), "l"(xa.x));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j]) : "l"(wr[j][2 * k4 + 1]), "l"(xa.y));
           }
+          xa = xb;
         }
+        float r[kOut];
 #pragma unroll
         for (int j = 0; j < kOut; ++j) {
-          const int o = threadIdx.x + j * nthr;
-          if (o < out_dim) y[(b0 + s) * out_dim + o] = acc[j];
+          float a0, a1;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc[j]));
+          r[j] = a0 + a1;
         }
+#pragma unroll
+        for (int j = 0; j < kOut; j += 4) yp[j / 4] = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
     }
   }
@@ -161,10 +202,11 @@ bool launch_extract_pilots(const float2* grid, float2* pilots, int32_t* counts, 
 
 bool launch_linear(const float* w, const float* bias, const float* x, float* y, int64_t batch, int in_dim, int out_dim, cudaStream_t st) {
   if (batch <= 0) return true;
-  if (in_dim == 24 && out_dim <= 2 * 864) {   // the reference configuration (24 pilots -> 1680 grid points)
+  if (in_dim == 24 && out_dim % 4 == 0 && out_dim <= 4 * 448 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
+    // the reference configuration (24 pilots -> 1680 grid points): 420 owner threads x 4 consecutive outputs
     int64_t nb = (batch + 63) / 64;
-    if (nb > 148) nb = 148;                   // 864 threads x 72 registers: one CTA per SM, grid-stride over sample groups
-    linear_regw_kernel<24, 2><<<(unsigned)nb, 864, 0, st>>>(w, bias, x, y, batch, out_dim);
+    if (nb > 148) nb = 148;                   // 14 warps x 128 registers: one CTA per SM, grid-stride over sample groups
+    linear_regw_kernel<24, 4, 448><<<(unsigned)nb, 448, 0, st>>>(w, bias, x, y, batch, out_dim);
     count_launch();
     return check_launch("linear_regw_kernel");
   }

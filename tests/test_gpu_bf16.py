@@ -190,6 +190,29 @@ def test_host_entry_point_bf16(sd):
         assert np.array_equal(y, yh), b
 
 
+def test_misaligned_output_is_rejected(sd):
+    """The estimates leave the head kernel as 16-byte vectors / bulk copies: `aft_forward` must refuse an output pointer
+    that is not 16-byte aligned (AFT_ERR_INVALID, nothing launched) instead of faulting on the device."""
+    m = util.make_model("forti", weights=util.forti_weights(sd), precision="bf16")
+    p, *_ = O.synthetic_batch(2, seed=5)
+    with torch.no_grad():
+        m(torch.from_numpy(p))                                     # creates the handle, loads the weights
+        lib = _capi.lib()
+        pil = torch.from_numpy(p).cuda().contiguous()
+        raw = torch.empty(2 * 120 * 14 * 8 + 64, dtype=torch.uint8, device="cuda")
+        ws = m._get_workspace(2, _capi.AFT_BF16)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        n0 = lib.aft_launch_count()
+        rc = lib.aft_forward(m._handle, C.c_void_p(pil.data_ptr()), None, None, None, C.c_void_p(raw.data_ptr() + 8), 2,
+                             _capi.AFT_BF16, C.c_void_p(ws_ptr), ws.numel() - (ws_ptr - ws.data_ptr()), st)
+        assert rc == _capi.AFT_ERR_INVALID and b"16-byte aligned" in lib.aft_last_error()
+        assert lib.aft_launch_count() == n0
+        torch.cuda.synchronize()
+        y = m(torch.from_numpy(p))                                 # the handle is still usable
+        assert torch.isfinite(torch.view_as_real(y)).all()
+
+
 def test_empty_batch_and_profile_api(sd):
     m = util.make_model("forti", weights=util.forti_weights(sd), precision="bf16")
     with torch.no_grad():
